@@ -1,0 +1,39 @@
+// rtow_main.cpp — what the reference's main.cpp (main.cpp:114-489) becomes on Linux with
+// the B200 path underneath: the same include list, the same scene-construction code
+// (scenes.h), the same `cam.render(world, lights)` call.  The Win32 shell glue of the
+// reference (file dialogs, ShellExecuteW) is out of scope.
+#include "rtweekend.h"
+
+#include "bvh.h"
+#include "hittable_list.h"
+#include "hittable.h"
+#include "sphere.h"
+#include "triangle.h"
+#include "camera.h"
+#include "quad.h"
+#include "point_light.h"
+#include "texture.h"
+#include "constant_medium.h"
+#include "mesh.h"
+
+#include "scenes.h"
+
+int main(int argc, char** argv) {
+    std::string scene = argc > 1 ? argv[1] : "specular";  // main.cpp:120 defaults to scene 7
+    std::string out = argc > 2 ? argv[2] : (scene + ".png");
+    scene_config cfg;
+    if (argc > 3) cfg.asset_dir = argv[3];
+    hittable_list world;
+    camera cam;
+    std::vector<point_light> lights;
+    if (!build_scene(scene, 1, world, cam, lights, cfg)) {
+        std::cerr << "unknown scene " << scene << std::endl;
+        return 1;
+    }
+    if (argc > 5) { cam.image_width = std::atoi(argv[4]); cam.aspect_ratio = double(cam.image_width) / std::atoi(argv[5]); }
+    if (argc > 6) cam.samples_per_pixel = std::atoi(argv[6]);
+    cam.image_name = out.c_str();
+    std::cout << "Rendering Image: " << cam.image_name << std::endl;
+    cam.render(world, lights);
+    return 0;
+}

@@ -1,0 +1,1127 @@
+// rt_b200.cu — the C ABI of include/rt_b200.h: scene upload (flatten -> bake -> SAH BVH ->
+// device layout) and the sm_100a kernels of the path-tracing hot path.
+//
+// Kernel inventory (all hand-written, no library kernels):
+//   render_kernel<STATS>   persistent megakernel: raygen -> traverse -> media -> shade ->
+//                          accumulate, with path regeneration (a lane whose path ended
+//                          starts its next sample in the same loop iteration) and 64-bit
+//                          fixed-point accumulation
+//   aov_kernel             deterministic primary hits (parity tests)
+//   resolve_kernel         accumulation buffer -> float radiance + RGB8 (Camera.txt:74-89)
+//   probe_*_kernel         per-function known-answer probes
+//   fma_peak_kernel        FP32 roofline denominator
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bvh_build.h"
+#include "rt_b200.h"
+#include "rt_device.cuh"
+
+using namespace rtdev;
+
+// ---------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------
+struct RenderArgs {
+    int width, height;
+    int max_depth;
+    int spp_begin;       // first sample index of this call
+    int n_local_samples; // samples this shard traces per pixel
+    int sample_stride, sample_offset;  // global sample = spp_begin + sample_offset + k * sample_stride
+    int seg_len;         // samples per work item
+    int n_segments;
+    int tiles_x, tiles_y, tile_size;
+    int tile_stride, tile_offset;      // global tile = tile_offset + k * tile_stride
+    int n_local_tiles;
+    int blocks_per_tile_x, blocks_per_tile_y;  // 8x4 pixel blocks per tile
+    unsigned long long n_items;
+    uint32_t k0, k1;
+};
+
+constexpr float kAccumScale = 268435456.0f;  // 2^RT_ACCUM_FRAC_BITS
+constexpr float kSampleClamp = 1048576.0f;   // 2^20: keeps 2^16 saturated samples inside 64 bits
+
+template <bool STATS>
+__global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A,
+                                                     unsigned long long* __restrict__ accum,
+                                                     unsigned long long* __restrict__ counters, Stats* __restrict__ gstats) {
+    const unsigned lane = threadIdx.x & 31u;
+    Stats st;
+    if (STATS) memset(&st, 0, sizeof st);
+    int overflow = 0;
+    unsigned long long dropped = 0;
+
+    while (true) {
+        // one work item per warp: an 8x4 pixel block x one segment of samples
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(&counters[0], 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= A.n_items) break;
+
+        const unsigned seg = (unsigned)(item % (unsigned long long)A.n_segments);
+        unsigned long long blk = item / (unsigned long long)A.n_segments;
+        const unsigned blocks_per_tile = (unsigned)(A.blocks_per_tile_x * A.blocks_per_tile_y);
+        const unsigned local_tile = (unsigned)(blk / blocks_per_tile);
+        const unsigned in_tile = (unsigned)(blk % blocks_per_tile);
+        const unsigned tile = A.tile_offset + local_tile * A.tile_stride;
+        const int tx = tile % A.tiles_x, ty = tile / A.tiles_x;
+        const int bx = in_tile % A.blocks_per_tile_x, by = in_tile / A.blocks_per_tile_x;
+        const int px = tx * A.tile_size + bx * 8 + (int)(lane & 7u);
+        const int py = ty * A.tile_size + by * 4 + (int)(lane >> 3);
+        const bool inside = px < A.width && py < A.height && (bx * 8 + (int)(lane & 7u)) < A.tile_size &&
+                            (by * 4 + (int)(lane >> 3)) < A.tile_size;
+        const uint32_t pixel = (uint32_t)(py * A.width + px);
+
+        int s = (int)seg * A.seg_len;
+        const int s_end = inside ? min(s + A.seg_len, A.n_local_samples) : s;
+
+        unsigned long long sum_r = 0, sum_g = 0, sum_b = 0;
+        Rng rng;
+        rng.pixel = pixel;
+        rng.k0 = A.k0;
+        rng.k1 = A.k1;
+        rng.sample = 0;
+        Ray ray;
+        V3 L = v3(0, 0, 0), T = v3(1, 1, 1);
+        uint32_t bounce = 0, origin_prim = PRIM_NONE;
+        bool alive = false;
+
+        while (true) {
+            if (!alive) {
+                if (s >= s_end) break;
+                rng.sample = (uint32_t)(A.spp_begin + A.sample_offset + s * A.sample_stride);
+                ray = camera_ray(S, px, py, rng);
+                L = v3(0, 0, 0);
+                T = v3(1, 1, 1);
+                bounce = 0;
+                origin_prim = PRIM_NONE;
+                alive = true;
+                if (STATS) st.samples++;
+            }
+            // ---- one bounce: Camera.txt:203-238 ------------------------------------
+            Hit hit;
+            traverse<STATS>(S, ray, 0.001f, __int_as_float(0x7f800000), origin_prim, hit, &st, &overflow);
+            int medium = -1;
+            if (S.n_media > 0) medium = media_hit<STATS>(S, ray, 0.001f, hit.t, rng, bounce, &st);
+
+            bool done = false;
+            if (medium < 0 && hit.prim == PRIM_NONE) {
+                L = L + T * v3(S.background);
+                done = true;
+            } else {
+                Surface sf;
+                if (medium >= 0) {  // constant_medium.h:45-50
+                    const DevMedium& md = S.media[medium];
+                    sf.p = fma3(hit.t, ray.d, ray.o);
+                    sf.normal = v3(md.normal);
+                    sf.front = true;
+                    sf.u = sf.v = 0.0f;
+                    sf.material = md.material;
+                    sf.prim_id = -1;
+                    origin_prim = PRIM_NONE;
+                } else {
+                    complete_hit(S, ray, hit, sf, false);
+                    origin_prim = hit.prim;
+                }
+                const DevMaterial& m = S.mats[sf.material];
+                L = L + T * mat_emitted(S, m, sf);
+                float4 u4 = make_float4(0, 0, 0, 0);
+                if (m.type != RT_MAT_DIFFUSE_LIGHT && m.type != RT_MAT_EMISSIVE_LIGHT) u4 = rng.draw(bounce, RS_SCATTER);
+                V3 att;
+                Ray next;
+                if (!mat_scatter(S, m, ray, sf, u4, att, next)) {
+                    done = true;
+                } else {
+                    if (S.n_lights > 0) L = L + T * att * point_lighting(S, sf.p, sf.normal);
+                    T = T * att;
+                    ray = next;
+                    bounce++;
+                    if (bounce >= (uint32_t)A.max_depth) done = true;  // ray_color(depth <= 0) returns 0
+                }
+            }
+            if (done) {
+                const bool finite = isfinite(L.x) && isfinite(L.y) && isfinite(L.z);
+                if (finite) {
+                    sum_r += __float2ull_rn(fminf(fmaxf(L.x, 0.0f), kSampleClamp) * kAccumScale);
+                    sum_g += __float2ull_rn(fminf(fmaxf(L.y, 0.0f), kSampleClamp) * kAccumScale);
+                    sum_b += __float2ull_rn(fminf(fmaxf(L.z, 0.0f), kSampleClamp) * kAccumScale);
+                } else {
+                    dropped++;
+                }
+                alive = false;
+                s++;
+            }
+        }
+        if (inside) {
+            unsigned long long* a = accum + 4ull * pixel;
+            atomicAdd(a + 0, sum_r);
+            atomicAdd(a + 1, sum_g);
+            atomicAdd(a + 2, sum_b);
+            if (dropped) { atomicAdd(a + 3, dropped); }
+        }
+        if (STATS) st.nonfinite += dropped;
+        dropped = 0;
+        __syncwarp();
+    }
+    if (overflow) atomicAdd(&counters[1], 1ull);
+    if (STATS) {
+        unsigned long long* g = reinterpret_cast<unsigned long long*>(gstats);
+        const unsigned long long* l = reinterpret_cast<const unsigned long long*>(&st);
+        for (unsigned i = 0; i < sizeof(Stats) / 8; i++) {
+            unsigned long long v = l[i];
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (lane == 0 && v) atomicAdd(g + i, v);
+        }
+    }
+}
+
+__global__ void aov_kernel(const __grid_constant__ DevScene S, int width, int height, int* __restrict__ prim_id,
+                           float* __restrict__ t_out, float* __restrict__ normal, float* __restrict__ point,
+                           float* __restrict__ uv, unsigned long long* counters) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= width || j >= height) return;
+    Ray ray;
+    ray.o = v3(S.center);
+    ray.d = fma3((float)i, v3(S.du), fma3((float)j, v3(S.dv), v3(S.dir00)));
+    ray.time = 0.0f;
+    Hit hit;
+    int overflow = 0;
+    traverse<false>(S, ray, 0.001f, __int_as_float(0x7f800000), PRIM_NONE, hit, nullptr, &overflow);
+    if (overflow) atomicAdd(&counters[1], 1ull);
+    size_t px = (size_t)j * width + i;
+    Surface sf;
+    sf.prim_id = -1;
+    sf.p = sf.normal = v3(0, 0, 0);
+    sf.u = sf.v = 0;
+    float t = 0.0f;
+    if (hit.prim != PRIM_NONE) {
+        complete_hit(S, ray, hit, sf, true);
+        t = hit.t;
+    }
+    if (prim_id) prim_id[px] = sf.prim_id;
+    if (t_out) t_out[px] = t;
+    if (normal) { normal[3 * px] = sf.normal.x; normal[3 * px + 1] = sf.normal.y; normal[3 * px + 2] = sf.normal.z; }
+    if (point) { point[3 * px] = sf.p.x; point[3 * px + 1] = sf.p.y; point[3 * px + 2] = sf.p.z; }
+    if (uv) { uv[2 * px] = sf.u; uv[2 * px + 1] = sf.v; }
+}
+
+// Camera.txt:74-89: scale by 1/spp, sqrt gamma, clamp [0, 0.999], int(255.999 * x)
+__global__ void resolve_kernel(const unsigned long long* __restrict__ accum, int n_pixels, double inv_scale_spp,
+                               float* __restrict__ rgb_linear, unsigned char* __restrict__ rgb8) {
+    int px = blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= n_pixels) return;
+    for (int c = 0; c < 3; c++) {
+        float lin = (float)((double)accum[4ull * px + c] * inv_scale_spp);
+        if (rgb_linear) rgb_linear[3ull * px + c] = lin;
+        if (rgb8) {
+            float g = lin > 0.0f ? sqrtf(lin) : 0.0f;
+            g = fminf(fmaxf(g, 0.0f), 0.999f);
+            rgb8[3ull * px + c] = (unsigned char)(int)(255.999f * g);
+        }
+    }
+}
+
+__global__ void probe_texture_kernel(const __grid_constant__ DevScene S, int tex, int n, const float* __restrict__ uvp,
+                                     float* __restrict__ rgb) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V3 c = tex_value(S, tex, uvp[5 * i], uvp[5 * i + 1], v3(uvp + 5 * i + 2));
+    rgb[3 * i] = c.x; rgb[3 * i + 1] = c.y; rgb[3 * i + 2] = c.z;
+}
+
+__global__ void probe_scatter_kernel(const __grid_constant__ DevScene S, int mat, int n, const float* __restrict__ in,
+                                     const float* __restrict__ uni, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = in + 16 * (size_t)i;
+    Ray ray;
+    ray.o = v3(r); ray.d = v3(r + 3); ray.time = r[6];
+    Surface sf;
+    sf.p = v3(r + 7); sf.normal = v3(r + 10); sf.front = r[13] != 0.0f; sf.u = r[14]; sf.v = r[15];
+    sf.material = mat; sf.prim_id = -1;
+    const DevMaterial& m = S.mats[mat];
+    V3 em = mat_emitted(S, m, sf);
+    float4 u4 = make_float4(uni[4 * i], uni[4 * i + 1], uni[4 * i + 2], uni[4 * i + 3]);
+    V3 att = v3(0, 0, 0);
+    Ray next;
+    next.o = next.d = v3(0, 0, 0);
+    next.time = 0;
+    bool ok = mat_scatter(S, m, ray, sf, u4, att, next);
+    float* o = out + 16 * (size_t)i;
+    o[0] = ok ? 1.0f : 0.0f;
+    o[1] = att.x; o[2] = att.y; o[3] = att.z;
+    o[4] = next.o.x; o[5] = next.o.y; o[6] = next.o.z;
+    o[7] = next.d.x; o[8] = next.d.y; o[9] = next.d.z;
+    o[10] = em.x; o[11] = em.y; o[12] = em.z;
+    o[13] = next.time; o[14] = o[15] = 0.0f;
+}
+
+__global__ void probe_hit_kernel(const __grid_constant__ DevScene S, int n, const float* __restrict__ rays, int* __restrict__ prim_id,
+                                 float* __restrict__ t_out, float* __restrict__ normal, float* __restrict__ uv,
+                                 unsigned long long* counters) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = rays + 9 * (size_t)i;
+    Ray ray;
+    ray.o = v3(r); ray.d = v3(r + 3); ray.time = r[6];
+    Hit hit;
+    int overflow = 0;
+    traverse<false>(S, ray, r[7], r[8], PRIM_NONE, hit, nullptr, &overflow);
+    if (overflow) atomicAdd(&counters[1], 1ull);
+    Surface sf;
+    sf.prim_id = -1;
+    sf.normal = v3(0, 0, 0);
+    sf.u = sf.v = 0;
+    if (hit.prim != PRIM_NONE) complete_hit(S, ray, hit, sf, true);
+    if (prim_id) prim_id[i] = sf.prim_id;
+    if (t_out) t_out[i] = hit.prim != PRIM_NONE ? hit.t : 0.0f;
+    if (normal) { normal[3 * i] = sf.normal.x; normal[3 * i + 1] = sf.normal.y; normal[3 * i + 2] = sf.normal.z; }
+    if (uv) { uv[2 * i] = sf.u; uv[2 * i + 1] = sf.v; }
+}
+
+// 8 independent FMA chains per thread: measures the FP32 issue roof (2 flops per FMA)
+__global__ void fma_peak_kernel(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+        x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+    float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 12345.678f) out[0] = s;
+}
+
+// ---------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct rt_ctx {
+    int device = 0;
+    std::string error;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<void*> scene_allocs;
+    DevScene scene{};
+    bool has_scene = false;
+    rt_camera camera{};
+    // accumulation
+    unsigned long long* accum = nullptr;
+    size_t accum_bytes = 0;
+    bool accum_external = false;
+    int acc_w = 0, acc_h = 0;
+    unsigned long long* counters = nullptr;  // [0] work counter, [1] overflow flag
+    Stats* dstats = nullptr;
+    rt_stats stats{};
+    int cam_w = 0, cam_h = 0;  // frame the device camera block was computed for
+    int sm_count = 0;
+    int blocks_per_sm[2] = {0, 0};
+    bool pending_async = false;
+};
+
+static int fail(rt_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));      \
+    } while (0)
+
+static void free_scene(rt_ctx* ctx) {
+    for (void* p : ctx->scene_allocs) cudaFree(p);
+    ctx->scene_allocs.clear();
+    ctx->has_scene = false;
+}
+
+template <class T>
+static int upload(rt_ctx* ctx, const std::vector<T>& v, const T** out) {
+    *out = nullptr;
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    void* p = nullptr;
+    CU(ctx, cudaMalloc(&p, bytes));
+    ctx->scene_allocs.push_back(p);
+    if (!v.empty()) CU(ctx, cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)p;
+    return RT_OK;
+}
+
+extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
+    if (!out) return RT_ERR_INVALID;
+    *out = nullptr;
+    rt_ctx* ctx = new (std::nothrow) rt_ctx();
+    if (!ctx) return RT_ERR_NOMEM;
+    *out = ctx;  // returned even on failure so that rt_last_error works; caller destroys it
+    if (n_devices != 1 || !device_ids) return fail(ctx, RT_ERR_INVALID, "rt_create: exactly one device per context (got %d)", n_devices);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(ctx, RT_ERR_CUDA, "rt_create: no CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    ctx->device = device_ids[0];
+    if (ctx->device < 0 || ctx->device >= count) return fail(ctx, RT_ERR_INVALID, "rt_create: device %d out of range", ctx->device);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CU(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    if (prop.major < 10) return fail(ctx, RT_ERR_CUDA, "rt_create: device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+    ctx->sm_count = prop.multiProcessorCount;
+    CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(ctx, cudaEventCreate(&ctx->ev0));
+    CU(ctx, cudaEventCreate(&ctx->ev1));
+    CU(ctx, cudaMalloc(&ctx->counters, 4 * sizeof(unsigned long long)));
+    CU(ctx, cudaMalloc(&ctx->dstats, sizeof(Stats)));
+    // local-memory traversal stacks live in L1: prefer L1 over shared memory
+    cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], render_kernel<false>, 256, 0));
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], render_kernel<true>, 256, 0));
+    cudaFuncAttributes fa;
+    CU(ctx, cudaFuncGetAttributes(&fa, render_kernel<false>));
+    ctx->stats.regs_per_thread = fa.numRegs;
+    ctx->stats.local_bytes_per_thread = (uint32_t)fa.localSizeBytes;
+    ctx->stats.threads_per_block = 256;
+    return RT_OK;
+}
+
+extern "C" void rt_destroy(rt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    if (ctx->accum && !ctx->accum_external) cudaFree(ctx->accum);
+    if (ctx->counters) cudaFree(ctx->counters);
+    if (ctx->dstats) cudaFree(ctx->dstats);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* rt_last_error(const rt_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+// ---------------------------------------------------------------------------------
+// scene upload
+// ---------------------------------------------------------------------------------
+namespace {
+
+struct D3 {
+    double x, y, z;
+};
+inline D3 d3(const double* p) { return D3{p[0], p[1], p[2]}; }
+inline D3 operator+(D3 a, D3 b) { return D3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline D3 operator-(D3 a, D3 b) { return D3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline D3 operator*(double s, D3 a) { return D3{s * a.x, s * a.y, s * a.z}; }
+inline double ddot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline D3 dcross(D3 a, D3 b) { return D3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline D3 dunit(D3 a) { return (1.0 / std::sqrt(ddot(a, a))) * a; }
+
+inline D3 xf_point(const rt_xform* x, D3 p) {
+    if (!x) return p;
+    return D3{x->r[0] * p.x + x->r[1] * p.y + x->r[2] * p.z + x->t[0], x->r[3] * p.x + x->r[4] * p.y + x->r[5] * p.z + x->t[1],
+              x->r[6] * p.x + x->r[7] * p.y + x->r[8] * p.z + x->t[2]};
+}
+inline D3 xf_dir(const rt_xform* x, D3 d) {
+    if (!x) return d;
+    return D3{x->r[0] * d.x + x->r[1] * d.y + x->r[2] * d.z, x->r[3] * d.x + x->r[4] * d.y + x->r[5] * d.z,
+              x->r[6] * d.x + x->r[7] * d.y + x->r[8] * d.z};
+}
+
+struct BakedPrim {
+    uint32_t dev_type;
+    int src_type, src_index;
+    int prim_id;  // canonical id (-1 for boundaries)
+    // world-space geometry in double
+    D3 a, b, c;   // sphere: c0, cvec, -; quad: Q, u, v; triangle: p0, p1, p2
+    double radius;
+    int material, xform;
+    float uv[6];
+};
+
+bool texture_needs_uv(const rt_scene_desc* sc, int tex, int depth = 0) {
+    if (tex < 0 || tex >= sc->n_textures || depth > 16) return false;
+    const rt_texture& t = sc->textures[tex];
+    if (t.type == RT_TEX_IMAGE || t.type == RT_TEX_CHECKER_TRIANGLE) return true;
+    if (t.type == RT_TEX_CHECKER) return texture_needs_uv(sc, t.even, depth + 1) || texture_needs_uv(sc, t.odd, depth + 1);
+    return false;
+}
+
+inline float __int_as_float_host(int v) {
+    float f;
+    std::memcpy(&f, &v, 4);
+    return f;
+}
+
+}  // namespace
+
+static int validate_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
+    if (!sc) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: null scene");
+    if (sc->struct_size != sizeof(rt_scene_desc) || sc->abi_version != RT_B200_ABI_VERSION)
+        return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: ABI mismatch (struct_size %u vs %zu, abi %u vs %d)", sc->struct_size,
+                    sizeof(rt_scene_desc), sc->abi_version, RT_B200_ABI_VERSION);
+    auto neg = [](int n) { return n < 0; };
+    if (neg(sc->n_world) || neg(sc->n_boundary_refs) || neg(sc->n_spheres) || neg(sc->n_quads) || neg(sc->n_triangles) ||
+        neg(sc->n_media) || neg(sc->n_xforms) || neg(sc->n_materials) || neg(sc->n_textures) || neg(sc->n_images) ||
+        neg(sc->n_perlins) || neg(sc->n_lights))
+        return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: negative count");
+    if (sc->n_world + sc->n_boundary_refs >= (1 << 25)) return fail(ctx, RT_ERR_UNSUPPORTED, "rt_upload_scene: more than 2^25 primitives");
+    auto check_ref = [&](const rt_prim_ref& r, bool boundary) -> const char* {
+        int n = r.type == RT_PRIM_SPHERE ? sc->n_spheres : r.type == RT_PRIM_QUAD ? sc->n_quads : r.type == RT_PRIM_TRIANGLE ? sc->n_triangles : -1;
+        if (n < 0) return "unknown primitive type";
+        if (r.index < 0 || r.index >= n) return "primitive index out of range";
+        int mat = r.type == RT_PRIM_SPHERE ? sc->spheres[r.index].material : r.type == RT_PRIM_QUAD ? sc->quads[r.index].material : sc->triangles[r.index].material;
+        int xf = r.type == RT_PRIM_SPHERE ? sc->spheres[r.index].xform : r.type == RT_PRIM_QUAD ? sc->quads[r.index].xform : sc->triangles[r.index].xform;
+        if (!boundary && (mat < 0 || mat >= sc->n_materials)) return "material index out of range";
+        if (xf < -1 || xf >= sc->n_xforms) return "xform index out of range";
+        return nullptr;
+    };
+    for (int i = 0; i < sc->n_world; i++)
+        if (const char* m = check_ref(sc->world[i], false)) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: world[%d]: %s", i, m);
+    for (int i = 0; i < sc->n_boundary_refs; i++)
+        if (const char* m = check_ref(sc->boundary_refs[i], true)) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: boundary_refs[%d]: %s", i, m);
+    for (int i = 0; i < sc->n_media; i++) {
+        const rt_medium& m = sc->media[i];
+        if (m.boundary_first < 0 || m.boundary_count < 0 || m.boundary_first + m.boundary_count > sc->n_boundary_refs)
+            return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: media[%d]: boundary range out of bounds", i);
+        if (m.material < 0 || m.material >= sc->n_materials) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: media[%d]: material out of range", i);
+        if (!(m.density > 0) || m.multiplicity < 1) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: media[%d]: density/multiplicity must be positive", i);
+        if (m.xform < -1 || m.xform >= sc->n_xforms) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: media[%d]: xform out of range", i);
+    }
+    for (int i = 0; i < sc->n_materials; i++) {
+        const rt_material& m = sc->materials[i];
+        if (m.type < RT_MAT_LAMBERTIAN || m.type > RT_MAT_SPECULAR) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: materials[%d]: unknown type %d", i, m.type);
+        bool textured = m.type == RT_MAT_LAMBERTIAN || m.type == RT_MAT_DIFFUSE_LIGHT || m.type == RT_MAT_EMISSIVE_LIGHT || m.type == RT_MAT_ISOTROPIC;
+        if (textured && (m.texture < 0 || m.texture >= sc->n_textures)) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: materials[%d]: texture out of range", i);
+    }
+    for (int i = 0; i < sc->n_textures; i++) {
+        const rt_texture& t = sc->textures[i];
+        if (t.type < RT_TEX_SOLID || t.type > RT_TEX_NOISE) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: textures[%d]: unknown type %d", i, t.type);
+        if ((t.type == RT_TEX_CHECKER || t.type == RT_TEX_CHECKER_TRIANGLE) && (t.even < 0 || t.even >= sc->n_textures || t.odd < 0 || t.odd >= sc->n_textures))
+            return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: textures[%d]: child out of range", i);
+        if (t.type == RT_TEX_IMAGE && t.image >= sc->n_images) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: textures[%d]: image out of range", i);
+        if (t.type == RT_TEX_NOISE && (t.perlin < 0 || t.perlin >= sc->n_perlins)) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: textures[%d]: perlin out of range", i);
+    }
+    for (int i = 0; i < sc->n_images; i++)
+        if (sc->images[i].width <= 0 || sc->images[i].height <= 0 || !sc->images[i].rgb) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: images[%d]: empty", i);
+    return RT_OK;
+}
+
+// Camera.txt:136-175 in double; stores the FP32 camera block for a width x height frame.
+static void setup_camera(rt_ctx* ctx, int width, int height) {
+    const rt_camera& c = ctx->camera;
+    const double pi = 3.1415926535897932385;
+    D3 lookfrom = d3(c.lookfrom), lookat = d3(c.lookat), vup = d3(c.vup);
+    double theta = c.vfov * pi / 180.0;
+    double h = std::tan(theta / 2);
+    double viewport_height = 2 * h * c.focus_dist;
+    double viewport_width = viewport_height * (double(width) / height);
+    D3 w = dunit(lookfrom - lookat);
+    D3 u = dunit(dcross(vup, w));
+    D3 v = dcross(w, u);
+    D3 viewport_u = viewport_width * u;
+    D3 viewport_v = viewport_height * (-1.0 * v);
+    D3 du = (1.0 / width) * viewport_u;
+    D3 dv = (1.0 / height) * viewport_v;
+    // pixel00_loc - center
+    D3 dir00 = (-c.focus_dist) * w - 0.5 * viewport_u - 0.5 * viewport_v + 0.5 * (du + dv);
+    double defocus_radius = c.focus_dist * std::tan((c.defocus_angle / 2) * pi / 180.0);
+    D3 disk_u = defocus_radius * u, disk_v = defocus_radius * v;
+    DevScene& S = ctx->scene;
+    auto put = [](float* dst, D3 s) { dst[0] = (float)s.x; dst[1] = (float)s.y; dst[2] = (float)s.z; };
+    put(S.center, lookfrom);
+    put(S.dir00, dir00);
+    put(S.du, du);
+    put(S.dv, dv);
+    put(S.disk_u, disk_u);
+    put(S.disk_v, disk_v);
+    put(S.background, d3(c.background));
+    S.defocus = c.defocus_angle > 0 ? 1 : 0;
+    ctx->cam_w = width;
+    ctx->cam_h = height;
+}
+
+extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
+    if (!ctx) return RT_ERR_INVALID;
+    auto t_begin = std::chrono::steady_clock::now();
+    int rc = validate_scene(ctx, sc);
+    if (rc != RT_OK) return rc;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (ctx->pending_async) { CU(ctx, cudaStreamSynchronize(ctx->stream)); ctx->pending_async = false; }
+    free_scene(ctx);
+
+    // ---- bake instance transforms, build per-primitive bounds -----------------------
+    std::vector<BakedPrim> baked;
+    baked.reserve((size_t)sc->n_world + sc->n_boundary_refs);
+    auto bake = [&](const rt_prim_ref& r, int prim_id) {
+        BakedPrim b{};
+        b.src_type = r.type;
+        b.src_index = r.index;
+        b.prim_id = prim_id;
+        if (r.type == RT_PRIM_SPHERE) {
+            const rt_sphere& s = sc->spheres[r.index];
+            const rt_xform* x = s.xform >= 0 ? &sc->xforms[s.xform] : nullptr;
+            b.a = xf_point(x, d3(s.center0));
+            b.b = xf_dir(x, d3(s.center_vec));
+            b.radius = s.radius;
+            b.material = s.material;
+            b.xform = s.xform;
+            bool moving = s.center_vec[0] != 0 || s.center_vec[1] != 0 || s.center_vec[2] != 0;
+            b.dev_type = moving ? PT_MSPHERE : PT_SPHERE;
+        } else if (r.type == RT_PRIM_QUAD) {
+            const rt_quad& q = sc->quads[r.index];
+            const rt_xform* x = q.xform >= 0 ? &sc->xforms[q.xform] : nullptr;
+            b.a = xf_point(x, d3(q.Q));
+            b.b = xf_dir(x, d3(q.u));
+            b.c = xf_dir(x, d3(q.v));
+            b.material = q.material;
+            b.xform = q.xform;
+            b.dev_type = PT_QUAD;
+        } else {
+            const rt_triangle& t = sc->triangles[r.index];
+            const rt_xform* x = t.xform >= 0 ? &sc->xforms[t.xform] : nullptr;
+            b.a = xf_point(x, d3(t.p0));
+            b.b = xf_point(x, d3(t.p1));
+            b.c = xf_point(x, d3(t.p2));
+            b.material = t.material;
+            b.xform = t.xform;
+            b.uv[0] = t.uv0[0]; b.uv[1] = t.uv0[1]; b.uv[2] = t.uv1[0]; b.uv[3] = t.uv1[1]; b.uv[4] = t.uv2[0]; b.uv[5] = t.uv2[1];
+            b.dev_type = PT_TRI;
+        }
+        baked.push_back(b);
+    };
+    for (int i = 0; i < sc->n_world; i++) bake(sc->world[i], i);
+    for (int i = 0; i < sc->n_boundary_refs; i++) bake(sc->boundary_refs[i], -1);
+
+    auto prim_box = [&](const BakedPrim& b, rtbvh::Box& box) {
+        auto grow = [&](D3 p, double pad) {
+            float lo[3] = {(float)(p.x - pad), (float)(p.y - pad), (float)(p.z - pad)};
+            float hi[3] = {(float)(p.x + pad), (float)(p.y + pad), (float)(p.z + pad)};
+            // (float) rounds to nearest: step one ulp outward so that the box stays conservative
+            for (int k = 0; k < 3; k++) { lo[k] = std::nextafter(lo[k], -INFINITY); hi[k] = std::nextafter(hi[k], INFINITY); }
+            box.grow(lo);
+            box.grow(hi);
+        };
+        if (b.dev_type == PT_SPHERE) {
+            grow(b.a, b.radius);
+        } else if (b.dev_type == PT_MSPHERE) {
+            grow(b.a, b.radius);
+            grow(b.a + b.b, b.radius);
+        } else if (b.dev_type == PT_QUAD) {
+            grow(b.a, 0); grow(b.a + b.b, 0); grow(b.a + b.c, 0); grow(b.a + b.b + b.c, 0);
+        } else {
+            grow(b.a, 0); grow(b.b, 0); grow(b.c, 0);
+        }
+    };
+
+    std::vector<rtbvh::Prim> prims((size_t)sc->n_world);
+    for (int i = 0; i < sc->n_world; i++) {
+        rtbvh::Prim& p = prims[i];
+        prim_box(baked[i], p.box);
+        for (int k = 0; k < 3; k++) p.centroid[k] = 0.5f * (p.box.lo[k] + p.box.hi[k]);
+        p.type = baked[i].dev_type;
+        p.index = (uint32_t)i;
+        p.cost = baked[i].dev_type == PT_SPHERE ? 1.0f : (baked[i].dev_type == PT_MSPHERE ? 1.2f : 1.3f);
+    }
+    rtbvh::Result bvh;
+    {
+        rtbvh::Builder builder(prims, bvh);
+        builder.run();
+    }
+
+    // ---- device arrays in leaf order, boundaries appended ------------------------------
+    std::vector<float4> sph, msph, quad, tri, tri_sh;
+    std::vector<double> sph_d, msph_d, quad_d, tri_d;
+    std::vector<int4> sph_sh, msph_sh, quad_sh;
+    std::vector<uint32_t> boundary_packed((size_t)sc->n_boundary_refs);
+    auto emit = [&](const BakedPrim& b) -> uint32_t {
+        if (b.dev_type == PT_SPHERE) {
+            sph.push_back(make_float4((float)b.a.x, (float)b.a.y, (float)b.a.z, (float)b.radius));
+            sph_d.insert(sph_d.end(), {b.a.x, b.a.y, b.a.z, b.radius});
+            sph_sh.push_back(make_int4(b.material, b.xform, b.prim_id, 0));
+            return (PT_SPHERE << 28) | (uint32_t)(sph.size() - 1);
+        } else if (b.dev_type == PT_MSPHERE) {
+            msph.push_back(make_float4((float)b.a.x, (float)b.a.y, (float)b.a.z, (float)b.radius));
+            msph.push_back(make_float4((float)b.b.x, (float)b.b.y, (float)b.b.z, 0.0f));
+            msph_d.insert(msph_d.end(), {b.a.x, b.a.y, b.a.z, b.radius, b.b.x, b.b.y, b.b.z, 0.0});
+            msph_sh.push_back(make_int4(b.material, b.xform, b.prim_id, 0));
+            return (PT_MSPHERE << 28) | (uint32_t)(msph_sh.size() - 1);
+        } else if (b.dev_type == PT_QUAD) {
+            // quad.h:13-21: n = u x v, normal = unit(n), D = normal.Q, w = n / (n.n)
+            D3 n = dcross(b.b, b.c);
+            D3 normal = dunit(n);
+            double D = ddot(normal, b.a);
+            D3 w = (1.0 / ddot(n, n)) * n;
+            D3 A = dcross(b.c, w), B = dcross(w, b.b);  // alpha = A.(p-Q), beta = B.(p-Q)
+            double a0 = ddot(A, b.a), b0 = ddot(B, b.a);
+            quad.push_back(make_float4((float)normal.x, (float)normal.y, (float)normal.z, (float)D));
+            quad.push_back(make_float4((float)A.x, (float)A.y, (float)A.z, (float)a0));
+            quad.push_back(make_float4((float)B.x, (float)B.y, (float)B.z, (float)b0));
+            quad_d.insert(quad_d.end(), {normal.x, normal.y, normal.z, D, A.x, A.y, A.z, a0, B.x, B.y, B.z, b0});
+            quad_sh.push_back(make_int4(b.material, 0, b.prim_id, 0));
+            return (PT_QUAD << 28) | (uint32_t)(quad_sh.size() - 1);
+        } else {
+            D3 e1 = b.b - b.a, e2 = b.c - b.a;
+            D3 normal = dunit(dcross(e1, e2));  // triangle.h:21-22
+            tri.push_back(make_float4((float)b.a.x, (float)b.a.y, (float)b.a.z, 0.0f));
+            tri.push_back(make_float4((float)e1.x, (float)e1.y, (float)e1.z, 0.0f));
+            tri.push_back(make_float4((float)e2.x, (float)e2.y, (float)e2.z, 0.0f));
+            tri_d.insert(tri_d.end(), {b.a.x, b.a.y, b.a.z, e1.x, e1.y, e1.z, e2.x, e2.y, e2.z});
+            tri_sh.push_back(make_float4((float)normal.x, (float)normal.y, (float)normal.z, __int_as_float_host(b.material)));
+            tri_sh.push_back(make_float4(b.uv[0], b.uv[1], b.uv[2], b.uv[3]));
+            tri_sh.push_back(make_float4(b.uv[4], b.uv[5], __int_as_float_host(b.prim_id), 0.0f));
+            return (PT_TRI << 28) | (uint32_t)(tri_sh.size() / 3 - 1);
+        }
+    };
+    for (uint32_t id : bvh.order) emit(baked[id]);
+    for (int i = 0; i < sc->n_boundary_refs; i++) boundary_packed[i] = emit(baked[(size_t)sc->n_world + i]);
+
+    // ---- tables ---------------------------------------------------------------------------
+    std::vector<DevMaterial> mats((size_t)sc->n_materials);
+    for (int i = 0; i < sc->n_materials; i++) {
+        const rt_material& m = sc->materials[i];
+        DevMaterial& d = mats[i];
+        d.type = m.type;
+        d.tex = m.texture;
+        for (int k = 0; k < 3; k++) d.albedo[k] = (float)m.albedo[k];
+        d.param = (float)m.param;
+        d.needs_uv = texture_needs_uv(sc, m.texture) ? 1 : 0;
+        d.pad = 0;
+    }
+    std::vector<DevTexture> texs((size_t)sc->n_textures);
+    for (int i = 0; i < sc->n_textures; i++) {
+        const rt_texture& t = sc->textures[i];
+        DevTexture& d = texs[i];
+        d.type = t.type;
+        d.a = t.type == RT_TEX_IMAGE ? t.image : (t.type == RT_TEX_NOISE ? t.perlin : t.even);
+        d.b = t.odd;
+        d.scale = (float)t.scale;
+        for (int k = 0; k < 3; k++) d.color[k] = (float)t.color[k];
+        d.pad = 0;
+    }
+    std::vector<DevImage> images((size_t)sc->n_images);
+    for (int i = 0; i < sc->n_images; i++) {
+        const rt_image& im = sc->images[i];
+        std::vector<unsigned char> bytes(im.rgb, im.rgb + (size_t)im.width * im.height * 3);
+        const unsigned char* dptr = nullptr;
+        rc = upload(ctx, bytes, &dptr);
+        if (rc != RT_OK) return rc;
+        images[i].rgb = dptr;
+        images[i].w = im.width;
+        images[i].h = im.height;
+    }
+    std::vector<float4> perlin_vec((size_t)sc->n_perlins * 256);
+    std::vector<unsigned char> perlin_perm((size_t)sc->n_perlins * 768);
+    for (int i = 0; i < sc->n_perlins; i++) {
+        const rt_perlin& p = sc->perlins[i];
+        for (int k = 0; k < 256; k++) {
+            perlin_vec[(size_t)i * 256 + k] = make_float4((float)p.randvec[k][0], (float)p.randvec[k][1], (float)p.randvec[k][2], 0.0f);
+            perlin_perm[(size_t)i * 768 + k] = (unsigned char)p.perm_x[k];
+            perlin_perm[(size_t)i * 768 + 256 + k] = (unsigned char)p.perm_y[k];
+            perlin_perm[(size_t)i * 768 + 512 + k] = (unsigned char)p.perm_z[k];
+        }
+    }
+    std::vector<DevMedium> media((size_t)sc->n_media);
+    for (int i = 0; i < sc->n_media; i++) {
+        const rt_medium& m = sc->media[i];
+        DevMedium& d = media[i];
+        std::memset(&d, 0, sizeof d);
+        d.bfirst = m.boundary_first;
+        d.bcount = m.boundary_count;
+        d.neg_inv_density = (float)(-1.0 / (m.density * m.multiplicity));
+        d.material = m.material;
+        D3 n = xf_dir(m.xform >= 0 ? &sc->xforms[m.xform] : nullptr, D3{1, 0, 0});
+        d.normal[0] = (float)n.x; d.normal[1] = (float)n.y; d.normal[2] = (float)n.z;
+    }
+    std::vector<DevLight> lights((size_t)sc->n_lights);
+    for (int i = 0; i < sc->n_lights; i++) {
+        const rt_point_light& l = sc->lights[i];
+        for (int k = 0; k < 3; k++) { lights[i].pos[k] = (float)l.position[k]; lights[i].intensity[k] = (float)l.intensity[k]; }
+        lights[i].size = (float)l.size;
+        lights[i].pad = 0;
+    }
+    std::vector<float> xrot((size_t)sc->n_xforms * 9);
+    for (int i = 0; i < sc->n_xforms; i++)
+        for (int k = 0; k < 9; k++) xrot[(size_t)i * 9 + k] = (float)sc->xforms[i].r[k];
+
+    std::vector<float4> nodes(bvh.nodes.size() * 4);
+    static_assert(sizeof(rtbvh::Node) == 64, "node layout");
+    std::memcpy(nodes.data(), bvh.nodes.data(), bvh.nodes.size() * 64);
+
+    DevScene& S = ctx->scene;
+    std::memset(&S, 0, sizeof S);
+#define UP(vec, field)                          \
+    rc = upload(ctx, vec, &S.field);            \
+    if (rc != RT_OK) return rc;
+    UP(nodes, nodes) UP(sph, sph) UP(msph, msph) UP(quad, quad) UP(tri, tri) UP(sph_d, sph_d) UP(msph_d, msph_d) UP(quad_d, quad_d)
+    UP(tri_d, tri_d) UP(sph_sh, sph_sh) UP(msph_sh, msph_sh) UP(quad_sh, quad_sh) UP(tri_sh, tri_sh) UP(xrot, xrot) UP(media, media)
+    UP(boundary_packed, boundary) UP(mats, mats) UP(texs, texs) UP(images, images) UP(perlin_vec, perlin_vec)
+    UP(perlin_perm, perlin_perm) UP(lights, lights)
+#undef UP
+    S.root = bvh.root;
+    S.n_nodes = (int)bvh.nodes.size();
+    S.n_media = sc->n_media;
+    S.n_lights = sc->n_lights;
+    ctx->camera = sc->camera;
+    ctx->cam_w = ctx->cam_h = 0;
+    ctx->has_scene = true;
+    ctx->stats.bvh_nodes = (uint32_t)bvh.nodes.size();
+    ctx->stats.bvh_depth = bvh.depth;
+    ctx->stats.bvh_leaves = bvh.leaves;
+    ctx->stats.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return RT_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// rendering
+// ---------------------------------------------------------------------------------
+static int ensure_accum(rt_ctx* ctx, int width, int height) {
+    size_t need = (size_t)width * height * 4 * sizeof(unsigned long long);
+    if (ctx->accum_external) {
+        if (ctx->acc_w != width || ctx->acc_h != height)
+            return fail(ctx, RT_ERR_STATE, "rt_render: bound accumulation buffer is %dx%d, frame is %dx%d", ctx->acc_w, ctx->acc_h, width, height);
+        return RT_OK;
+    }
+    if (ctx->accum && ctx->acc_w == width && ctx->acc_h == height) return RT_OK;
+    if (ctx->accum) cudaFree(ctx->accum);
+    ctx->accum = nullptr;
+    cudaError_t e = cudaMalloc(&ctx->accum, need);
+    if (e != cudaSuccess) return fail(ctx, RT_ERR_NOMEM, "rt_render: cannot allocate %zu bytes for the accumulation buffer", need);
+    ctx->accum_bytes = need;
+    ctx->acc_w = width;
+    ctx->acc_h = height;
+    cudaMemsetAsync(ctx->accum, 0, need, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    return RT_OK;
+}
+
+extern "C" int rt_bind_accum(rt_ctx* ctx, void* device_ptr, size_t bytes, int32_t width, int32_t height) {
+    if (!ctx) return RT_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (ctx->accum && !ctx->accum_external) cudaFree(ctx->accum);
+    ctx->accum = nullptr;
+    ctx->accum_external = false;
+    ctx->acc_w = ctx->acc_h = 0;
+    ctx->accum_bytes = 0;
+    if (!device_ptr) return RT_OK;
+    size_t need = (size_t)width * height * 4 * sizeof(unsigned long long);
+    if (width <= 0 || height <= 0 || bytes < need) return fail(ctx, RT_ERR_INVALID, "rt_bind_accum: need %zu bytes for %dx%d, got %zu", need, width, height, bytes);
+    ctx->accum = (unsigned long long*)device_ptr;
+    ctx->accum_external = true;
+    ctx->accum_bytes = need;
+    ctx->acc_w = width;
+    ctx->acc_h = height;
+    return RT_OK;
+}
+
+extern "C" int rt_accum_buffer(rt_ctx* ctx, void** device_ptr, size_t* bytes) {
+    if (!ctx || !device_ptr || !bytes) return RT_ERR_INVALID;
+    if (!ctx->accum) return fail(ctx, RT_ERR_STATE, "rt_accum_buffer: nothing rendered or bound yet");
+    *device_ptr = ctx->accum;
+    *bytes = ctx->accum_bytes;
+    return RT_OK;
+}
+
+extern "C" int rt_sync(rt_ctx* ctx) {
+    if (!ctx) return RT_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaDeviceSynchronize());
+    ctx->pending_async = false;
+    unsigned long long c[2] = {0, 0};
+    CU(ctx, cudaMemcpy(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost));
+    if (c[1]) return fail(ctx, RT_ERR_KERNEL, "traversal stack overflow (BVH deeper than %d)", STACK_SIZE);
+    return RT_OK;
+}
+
+extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (!p || p->struct_size != sizeof(rt_render_params)) return fail(ctx, RT_ERR_INVALID, "rt_render: bad params struct");
+    if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "rt_render: no scene uploaded");
+    if (p->width <= 0 || p->height <= 0 || p->samples_per_pixel <= 0 || p->max_depth < 0 || p->spp_begin < 0)
+        return fail(ctx, RT_ERR_INVALID, "rt_render: width/height/samples must be positive");
+    if ((long long)p->width * p->height >= (1ll << 31)) return fail(ctx, RT_ERR_UNSUPPORTED, "rt_render: frame too large");
+    const int count = p->shard_count <= 1 ? 1 : p->shard_count;
+    const int rank = count == 1 ? 0 : p->shard_rank;
+    if (rank < 0 || rank >= count) return fail(ctx, RT_ERR_INVALID, "rt_render: shard_rank %d outside [0,%d)", rank, count);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t stream = p->stream ? (cudaStream_t)p->stream : ctx->stream;
+    int rc = ensure_accum(ctx, p->width, p->height);
+    if (rc != RT_OK) return rc;
+    if (ctx->cam_w != p->width || ctx->cam_h != p->height) setup_camera(ctx, p->width, p->height);
+
+    RenderArgs A;
+    std::memset(&A, 0, sizeof A);
+    A.width = p->width;
+    A.height = p->height;
+    A.max_depth = p->max_depth;
+    A.spp_begin = p->spp_begin;
+    A.tile_size = p->tile_size > 0 ? p->tile_size : 16;
+    if (A.tile_size % 8 != 0) return fail(ctx, RT_ERR_INVALID, "rt_render: tile_size must be a multiple of 8");
+    A.tiles_x = (p->width + A.tile_size - 1) / A.tile_size;
+    A.tiles_y = (p->height + A.tile_size - 1) / A.tile_size;
+    A.blocks_per_tile_x = A.tile_size / 8;
+    A.blocks_per_tile_y = A.tile_size / 4;
+    const int n_tiles = A.tiles_x * A.tiles_y;
+    int mode = p->shard_mode;
+    if (mode == RT_SHARD_AUTO) mode = (n_tiles / count >= 256) ? RT_SHARD_TILES : RT_SHARD_SAMPLES;
+    if (count == 1) mode = RT_SHARD_TILES;
+    if (mode == RT_SHARD_TILES) {
+        A.tile_stride = count;
+        A.tile_offset = rank;
+        A.n_local_tiles = (n_tiles - rank + count - 1) / count;
+        A.sample_stride = 1;
+        A.sample_offset = 0;
+        A.n_local_samples = p->samples_per_pixel;
+    } else if (mode == RT_SHARD_SAMPLES) {
+        A.tile_stride = 1;
+        A.tile_offset = 0;
+        A.n_local_tiles = n_tiles;
+        A.sample_stride = count;
+        A.sample_offset = rank;
+        A.n_local_samples = (p->samples_per_pixel - rank + count - 1) / count;
+    } else {
+        return fail(ctx, RT_ERR_INVALID, "rt_render: unknown shard_mode %d", p->shard_mode);
+    }
+    const bool stats = (p->flags & RT_FLAG_STATS) != 0;
+    const int bps = ctx->blocks_per_sm[stats ? 1 : 0];
+    const int grid = ctx->sm_count * (bps > 0 ? bps : 1);
+    // segment length: enough work items to keep every resident warp busy ~8 times over,
+    // but never shorter than 1 sample (fixed-point sums make the split result-neutral)
+    const unsigned long long pixel_blocks = (unsigned long long)A.n_local_tiles * A.blocks_per_tile_x * A.blocks_per_tile_y;
+    const unsigned long long resident_warps = (unsigned long long)grid * 8ull;
+    int n_seg = 1;
+    if (A.n_local_samples > 0 && pixel_blocks > 0) {
+        unsigned long long want = (resident_warps * 8ull + pixel_blocks - 1) / pixel_blocks;
+        if (want < 1) want = 1;
+        if (want > (unsigned long long)A.n_local_samples) want = A.n_local_samples;
+        n_seg = (int)want;
+    }
+    A.seg_len = A.n_local_samples > 0 ? (A.n_local_samples + n_seg - 1) / n_seg : 1;
+    A.n_segments = A.n_local_samples > 0 ? (A.n_local_samples + A.seg_len - 1) / A.seg_len : 0;
+    A.n_items = pixel_blocks * (unsigned long long)A.n_segments;
+    A.k0 = (uint32_t)(p->seed & 0xffffffffu);
+    A.k1 = (uint32_t)(p->seed >> 32);
+
+    if (!(p->flags & RT_FLAG_ACCUMULATE)) CU(ctx, cudaMemsetAsync(ctx->accum, 0, (size_t)p->width * p->height * 32, stream));
+    CU(ctx, cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), stream));
+    if (stats) CU(ctx, cudaMemsetAsync(ctx->dstats, 0, sizeof(Stats), stream));
+    const bool async = (p->flags & RT_FLAG_ASYNC) != 0;
+    if (!async) CU(ctx, cudaEventRecord(ctx->ev0, stream));
+    ctx->stats.kernel_launches = 0;
+    if (A.n_items > 0) {
+        if (stats) render_kernel<true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+        else render_kernel<false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+        CU(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches = 1;
+    }
+    ctx->stats.blocks = grid;
+    ctx->stats.samples = (uint64_t)A.n_local_samples * ((mode == RT_SHARD_TILES && count > 1) ? 0 : (uint64_t)p->width * p->height);
+    if (mode == RT_SHARD_TILES && count > 1) {
+        // pixels owned by this shard
+        uint64_t px = 0;
+        for (int t = rank; t < n_tiles; t += count) {
+            int tx = t % A.tiles_x, ty = t / A.tiles_x;
+            int w = std::min(A.tile_size, p->width - tx * A.tile_size), h = std::min(A.tile_size, p->height - ty * A.tile_size);
+            px += (uint64_t)w * h;
+        }
+        ctx->stats.samples = px * (uint64_t)A.n_local_samples;
+    }
+    if (async) {
+        ctx->pending_async = true;
+        return RT_OK;
+    }
+    CU(ctx, cudaEventRecord(ctx->ev1, stream));
+    CU(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0;
+    CU(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.render_ms = ms;
+    unsigned long long c[2] = {0, 0};
+    CU(ctx, cudaMemcpy(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost));
+    if (c[1]) return fail(ctx, RT_ERR_KERNEL, "traversal stack overflow (BVH deeper than %d)", STACK_SIZE);
+    if (stats) {
+        Stats h;
+        CU(ctx, cudaMemcpy(&h, ctx->dstats, sizeof h, cudaMemcpyDeviceToHost));
+        ctx->stats.rays = h.rays;
+        ctx->stats.node_visits = h.node_visits;
+        ctx->stats.box_tests = h.box_tests;
+        ctx->stats.sphere_tests = h.sphere_tests;
+        ctx->stats.quad_tests = h.quad_tests;
+        ctx->stats.triangle_tests = h.tri_tests;
+        ctx->stats.medium_queries = h.medium_queries;
+        ctx->stats.boundary_tests = h.boundary_tests;
+        ctx->stats.fp64_sphere_tests = h.fp64_sphere;
+        ctx->stats.nonfinite_samples = h.nonfinite;
+    }
+    return RT_OK;
+}
+
+extern "C" int rt_download(rt_ctx* ctx, int32_t total_spp, float* rgb_linear, uint8_t* rgb8) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (!ctx->accum) return fail(ctx, RT_ERR_STATE, "rt_download: nothing rendered yet");
+    if (total_spp <= 0) return fail(ctx, RT_ERR_INVALID, "rt_download: total_spp must be positive");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaDeviceSynchronize());
+    ctx->pending_async = false;
+    const int n = ctx->acc_w * ctx->acc_h;
+    float* dlin = nullptr;
+    unsigned char* d8 = nullptr;
+    if (rgb_linear) CU(ctx, cudaMalloc(&dlin, (size_t)n * 3 * sizeof(float)));
+    if (rgb8) CU(ctx, cudaMalloc(&d8, (size_t)n * 3));
+    double inv = 1.0 / ((double)kAccumScale * (double)total_spp);
+    resolve_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->accum, n, inv, dlin, d8);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && rgb_linear) e = cudaMemcpy(rgb_linear, dlin, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rgb8) e = cudaMemcpy(rgb8, d8, (size_t)n * 3, cudaMemcpyDeviceToHost);
+    if (dlin) cudaFree(dlin);
+    if (d8) cudaFree(d8);
+    if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "rt_download: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
+extern "C" int rt_render_aov(rt_ctx* ctx, int32_t width, int32_t height, int32_t* prim_id, float* t, float* normal, float* point,
+                             float* uv) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "rt_render_aov: no scene uploaded");
+    if (width <= 0 || height <= 0) return fail(ctx, RT_ERR_INVALID, "rt_render_aov: bad frame size");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (ctx->cam_w != width || ctx->cam_h != height) setup_camera(ctx, width, height);
+    const size_t n = (size_t)width * height;
+    int* d_id = nullptr;
+    float *d_t = nullptr, *d_n = nullptr, *d_p = nullptr, *d_uv = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void** p, size_t bytes, const void* want) {
+        if (want && e == cudaSuccess) e = cudaMalloc(p, bytes);
+    };
+    alloc((void**)&d_id, n * 4, prim_id);
+    alloc((void**)&d_t, n * 4, t);
+    alloc((void**)&d_n, n * 12, normal);
+    alloc((void**)&d_p, n * 12, point);
+    alloc((void**)&d_uv, n * 8, uv);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) {
+        dim3 block(8, 8), grid((width + 7) / 8, (height + 7) / 8);
+        aov_kernel<<<grid, block, 0, ctx->stream>>>(ctx->scene, width, height, d_id, d_t, d_n, d_p, d_uv, ctx->counters);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    auto fetch = [&](void* dst, const void* src, size_t bytes) {
+        if (dst && e == cudaSuccess) e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+    };
+    fetch(prim_id, d_id, n * 4);
+    fetch(t, d_t, n * 4);
+    fetch(normal, d_n, n * 12);
+    fetch(point, d_p, n * 12);
+    fetch(uv, d_uv, n * 8);
+    cudaFree(d_id); cudaFree(d_t); cudaFree(d_n); cudaFree(d_p); cudaFree(d_uv);
+    if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "rt_render_aov: %s", cudaGetErrorString(e));
+    unsigned long long c[2] = {0, 0};
+    CU(ctx, cudaMemcpy(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost));
+    if (c[1]) return fail(ctx, RT_ERR_KERNEL, "traversal stack overflow (BVH deeper than %d)", STACK_SIZE);
+    return RT_OK;
+}
+
+extern "C" int rt_get_stats(rt_ctx* ctx, rt_stats* out) {
+    if (!ctx || !out) return RT_ERR_INVALID;
+    *out = ctx->stats;
+    return RT_OK;
+}
+
+extern "C" int rt_measure_fp32_peak(rt_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return RT_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    float* d = nullptr;
+    CU(ctx, cudaMalloc(&d, 16));
+    const int iters = 1 << 16, threads = 1024, blocks = ctx->sm_count * 2;
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        fma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters, 1.0000001f, 1e-7f);
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaError_t e = cudaEventSynchronize(ctx->ev1);
+        if (e != cudaSuccess) { cudaFree(d); return fail(ctx, RT_ERR_CUDA, "rt_measure_fp32_peak: %s", cudaGetErrorString(e)); }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        double flops = 2.0 * 8.0 * iters * (double)threads * blocks;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    }
+    cudaFree(d);
+    *tflops = best;
+    return RT_OK;
+}
+
+// ---- probes -----------------------------------------------------------------------
+template <class Launch>
+static int run_probe(rt_ctx* ctx, const char* name, const std::vector<std::pair<const void*, size_t>>& inputs,
+                     const std::vector<std::pair<void*, size_t>>& outputs, Launch launch) {
+    CU(ctx, cudaSetDevice(ctx->device));
+    std::vector<void*> din(inputs.size(), nullptr), dout(outputs.size(), nullptr);
+    cudaError_t e = cudaSuccess;
+    for (size_t i = 0; i < inputs.size() && e == cudaSuccess; i++) {
+        e = cudaMalloc(&din[i], std::max<size_t>(inputs[i].second, 16));
+        if (e == cudaSuccess && inputs[i].second) e = cudaMemcpy(din[i], inputs[i].first, inputs[i].second, cudaMemcpyHostToDevice);
+    }
+    for (size_t i = 0; i < outputs.size() && e == cudaSuccess; i++)
+        if (outputs[i].first) e = cudaMalloc(&dout[i], std::max<size_t>(outputs[i].second, 16));
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) {
+        launch(din, dout);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    for (size_t i = 0; i < outputs.size() && e == cudaSuccess; i++)
+        if (outputs[i].first) e = cudaMemcpy(outputs[i].first, dout[i], outputs[i].second, cudaMemcpyDeviceToHost);
+    for (void* p : din) cudaFree(p);
+    for (void* p : dout) cudaFree(p);
+    if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e));
+    return RT_OK;
+}
+
+extern "C" int rt_probe_texture(rt_ctx* ctx, int32_t texture, int32_t n, const float* uvp, float* rgb) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "rt_probe_texture: no scene uploaded");
+    if (n <= 0 || !uvp || !rgb) return fail(ctx, RT_ERR_INVALID, "rt_probe_texture: bad arguments");
+    return run_probe(ctx, "rt_probe_texture", {{uvp, (size_t)n * 20}}, {{rgb, (size_t)n * 12}},
+                     [&](std::vector<void*>& in, std::vector<void*>& out) {
+                         probe_texture_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, texture, n, (const float*)in[0], (float*)out[0]);
+                     });
+}
+
+extern "C" int rt_probe_scatter(rt_ctx* ctx, int32_t material, int32_t n, const float* in_rec, const float* uniforms, float* out_rec) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "rt_probe_scatter: no scene uploaded");
+    if (n <= 0 || !in_rec || !uniforms || !out_rec) return fail(ctx, RT_ERR_INVALID, "rt_probe_scatter: bad arguments");
+    return run_probe(ctx, "rt_probe_scatter", {{in_rec, (size_t)n * 64}, {uniforms, (size_t)n * 16}}, {{out_rec, (size_t)n * 64}},
+                     [&](std::vector<void*>& in, std::vector<void*>& out) {
+                         probe_scatter_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, material, n, (const float*)in[0],
+                                                                                         (const float*)in[1], (float*)out[0]);
+                     });
+}
+
+extern "C" int rt_probe_hit(rt_ctx* ctx, int32_t n, const float* rays, int32_t* prim_id, float* t, float* normal, float* uv) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "rt_probe_hit: no scene uploaded");
+    if (n <= 0 || !rays) return fail(ctx, RT_ERR_INVALID, "rt_probe_hit: bad arguments");
+    int rc = run_probe(ctx, "rt_probe_hit", {{rays, (size_t)n * 36}},
+                       {{prim_id, (size_t)n * 4}, {t, (size_t)n * 4}, {normal, (size_t)n * 12}, {uv, (size_t)n * 8}},
+                       [&](std::vector<void*>& in, std::vector<void*>& out) {
+                           probe_hit_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, n, (const float*)in[0], (int*)out[0],
+                                                                                       (float*)out[1], (float*)out[2], (float*)out[3],
+                                                                                       ctx->counters);
+                       });
+    return rc;
+}

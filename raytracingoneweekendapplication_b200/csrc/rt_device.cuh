@@ -1,0 +1,682 @@
+// rt_device.cuh — device-side data layout and the hot-path functions of the path tracer
+// (sm_100a).  Everything here is FP32 unless a function says otherwise.
+//
+// Layout in HBM (all read-only during a render, fetched through the non-coherent path,
+// L1/L2 resident for every BASELINE scene; see DESIGN.md "data layout"):
+//   nodes      interior BVH2 nodes, 64 B = 4 x float4:
+//                {L.min, link_L} {L.max, link_R} {R.min, -} {R.max, -}
+//              link >= 0: interior node index; link < 0: leaf, ~link =
+//                type<<28 | (count-1)<<25 | first     (first indexes the typed array)
+//   sph        static spheres, 16 B  {c.xyz, r}
+//   msph       moving spheres, 32 B  {c0.xyz, r} {cvec.xyz, 0}
+//   quad       48 B  {n.xyz, D} {A.xyz, a0} {B.xyz, b0}   alpha = A.P - a0, beta = B.P - b0
+//   tri        48 B  {p0.xyz, 0} {e1.xyz, 0} {e2.xyz, 0}
+//   *_d        FP64 copies used by the near-surface / near-edge refinement paths
+//   *_sh       shading records fetched once per accepted hit
+// Typed arrays are stored in BVH leaf order, so a leaf's primitives are contiguous and
+// there is no index indirection.  Media boundaries live at the tail of the same arrays.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rt_b200.h"
+
+namespace rtdev {
+
+enum : uint32_t { PT_SPHERE = 0, PT_MSPHERE = 1, PT_QUAD = 2, PT_TRI = 3 };
+constexpr uint32_t PRIM_NONE = 0xffffffffu;
+constexpr int STACK_SIZE = 48;
+
+struct DevMaterial {  // 32 B
+    int type;
+    int tex;
+    float albedo[3];
+    float param;
+    int needs_uv;  // the texture chain reads (u,v): sphere UVs are only computed then
+    int pad;
+};
+struct DevTexture {  // 32 B
+    int type;
+    int a;  // checker: even, image: image index, noise: perlin index
+    int b;  // checker: odd
+    float scale;
+    float color[3];
+    int pad;
+};
+struct DevImage {
+    const unsigned char* rgb;
+    int w, h;
+};
+struct DevMedium {  // 48 B
+    int bfirst, bcount;  // range in `boundary`
+    float neg_inv_density;  // -1 / (multiplicity * density)
+    int material;
+    float normal[3];  // R * (1,0,0)
+    int pad;
+    float bmin[3];
+    float bmax_pad;
+};
+struct DevLight {
+    float pos[3];
+    float size;
+    float intensity[3];
+    float pad;
+};
+
+struct DevScene {
+    const float4* nodes;
+    int root;
+    int n_nodes;
+    const float4* sph;
+    const float4* msph;
+    const float4* quad;
+    const float4* tri;
+    const double* sph_d;   // 4 per sphere: c, r
+    const double* msph_d;  // 8 per sphere: c0, r, cvec, 0
+    const double* quad_d;  // 12 per quad: n, D, A, a0, B, b0
+    const double* tri_d;   // 9 per triangle: p0, e1, e2
+    const int4* sph_sh;    // {material, xform, prim id, 0}
+    const int4* msph_sh;
+    const int4* quad_sh;   // {material, 0, prim id, 0}
+    const float4* tri_sh;  // 3 per triangle: {n.xyz, as_float(material)} {uv0, uv1} {uv2, as_float(id), 0}
+    const float* xrot;     // 9 per xform: world-from-object rotation, row-major
+    const DevMedium* media;
+    int n_media;
+    const uint32_t* boundary;  // packed prim refs type<<28 | index
+    const DevMaterial* mats;
+    const DevTexture* texs;
+    const DevImage* images;
+    const float4* perlin_vec;          // 256 per perlin
+    const unsigned char* perlin_perm;  // 768 per perlin: perm_x, perm_y, perm_z
+    const DevLight* lights;
+    int n_lights;
+    // camera (Camera.txt:136-175, evaluated in double on the host)
+    float center[3], dir00[3], du[3], dv[3], disk_u[3], disk_v[3];
+    float background[3];
+    int defocus;
+};
+
+struct Stats {
+    unsigned long long rays, node_visits, box_tests, sphere_tests, quad_tests, tri_tests, medium_queries,
+        boundary_tests, fp64_sphere, nonfinite, samples;
+};
+
+// ---------------------------------------------------------------------------------
+// small vector helpers
+// ---------------------------------------------------------------------------------
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 v3(const float* p) { return V3{p[0], p[1], p[2]}; }
+__device__ __forceinline__ V3 v3(float4 f) { return V3{f.x, f.y, f.z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a) { return V3{-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return V3{s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return V3{s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+    return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ V3 fma3(float s, V3 a, V3 b) { return V3{fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)}; }
+__device__ __forceinline__ V3 normalize(V3 a) { return rsqrtf(dot(a, a)) * a; }
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// ---------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter = (pixel, sample, bounce<<8 | stream, 0),
+// key = seed.  The image is a pure function of these, which is what makes 1/2/4/8-GPU
+// renders bit-identical.  Dimension assignment (shared with oracle/philox_ref.h):
+//   stream 0        camera: x = jitter x, y = jitter y, z = ray time
+//   stream 1..15    defocus-disk rejection attempts, two per block ((x,y) then (z,w))
+//   stream 16       scatter: x,y,z = random_unit_vector's cube point, w = dielectric test
+//   stream 32 + k   media 4k..4k+3: one free-flight uniform each
+// ---------------------------------------------------------------------------------
+constexpr uint32_t RS_CAMERA = 0, RS_DEFOCUS = 1, RS_SCATTER = 16, RS_MEDIUM = 32;
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// 24-bit uniform in [0,1): exactly representable in FP32 and identical in the FP64 oracle
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
+
+struct Rng {
+    uint32_t pixel, sample, k0, k1;
+    __device__ __forceinline__ float4 draw(uint32_t bounce, uint32_t stream) const {
+        uint4 r = philox4x32_10(pixel, sample, (bounce << 8) | stream, 0u, k0, k1);
+        return make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+    }
+};
+
+// ---------------------------------------------------------------------------------
+// ray + hit
+// ---------------------------------------------------------------------------------
+struct Ray {
+    V3 o, d;
+    float time;
+};
+struct Hit {
+    float t;
+    uint32_t prim;  // type<<28 | index, PRIM_NONE = miss
+    float u, v;     // quad: alpha, beta; triangle: barycentric u, v
+};
+
+// sphere.h:32-49.  Robust FP32 form (distance from the centre to the ray line instead of
+// h*h - a*c), the exact c = 0 case for a ray that starts ON this sphere, and the
+// reference's own double-precision quadratic when the origin is within r/16 of the
+// surface of a sphere it did not start on (large ground spheres).
+template <bool STATS>
+__device__ __forceinline__ void hit_sphere(V3 c, float r, const double* cd, bool moving, bool self, const Ray& ray, float inv_a,
+                                           float tmin, uint32_t prim, Hit& hit, Stats* st) {
+    V3 oc = c - ray.o;
+    float h = dot(ray.d, oc);
+    float k = h * inv_a;
+    float r2 = r * r;
+    float t0, t1;
+    if (self) {
+        t0 = -1.0f;  // the root at the origin (exactly 0 in the reference up to 1e-13)
+        t1 = 2.0f * k;
+    } else {
+        float cterm = dot(oc, oc) - r2;
+        if (fabsf(cterm) < 0.125f * r2) {
+            if (STATS) st->fp64_sphere++;
+            double cx = cd[0], cy = cd[1], cz = cd[2], rr = cd[3];
+            if (moving) {  // sphere.h:33 in double
+                cx += (double)ray.time * cd[4]; cy += (double)ray.time * cd[5]; cz += (double)ray.time * cd[6];
+            }
+            double ox = cx - (double)ray.o.x, oy = cy - (double)ray.o.y, oz = cz - (double)ray.o.z;
+            double dx = ray.d.x, dy = ray.d.y, dz = ray.d.z;
+            double a = dx * dx + dy * dy + dz * dz;
+            double hh = dx * ox + dy * oy + dz * oz;
+            double cc = ox * ox + oy * oy + oz * oz - rr * rr;
+            double disc = hh * hh - a * cc;
+            if (disc < 0.0) return;
+            double sq = sqrt(disc);
+            t0 = (float)((hh - sq) / a);
+            t1 = (float)((hh + sq) / a);
+        } else {
+            V3 l = fma3(-k, ray.d, oc);
+            float disc = r2 - dot(l, l);
+            if (disc < 0.0f) return;
+            float sq = sqrtf(disc * inv_a);
+            t0 = k - sq;
+            t1 = k + sq;
+        }
+    }
+    float t = t0;
+    if (!(t > tmin && t < hit.t)) {  // interval::surrounds (sphere.h:45-48)
+        t = t1;
+        if (!(t > tmin && t < hit.t)) return;
+    }
+    hit.t = t;
+    hit.prim = prim;
+}
+
+// quad.h:29-73 with alpha = w.(p x v) rewritten as (v x w).p (A = v x w, B = w x u)
+__device__ __forceinline__ void hit_quad(float4 q0, float4 q1, float4 q2, const Ray& ray, float tmin, uint32_t prim, Hit& hit) {
+    V3 n = v3(q0);
+    float denom = dot(n, ray.d);
+    if (fabsf(denom) < 1e-8f) return;
+    float t = __fdividef(q0.w - dot(n, ray.o), denom);
+    if (!(t >= tmin && t <= hit.t)) return;  // interval::contains (quad.h:39)
+    V3 p = fma3(t, ray.d, ray.o);
+    float alpha = dot(v3(q1), p) - q1.w;
+    float beta = dot(v3(q2), p) - q2.w;
+    if (alpha < 0.0f || alpha > 1.0f || beta < 0.0f || beta > 1.0f) return;
+    hit.t = t;
+    hit.prim = prim;
+    hit.u = alpha;
+    hit.v = beta;
+}
+
+// triangle.h:65-113 (Moeller-Trumbore, two-sided, edges precomputed)
+__device__ __forceinline__ void hit_tri(float4 t0, float4 t1, float4 t2, const Ray& ray, float tmin, uint32_t prim, Hit& hit) {
+    V3 e1 = v3(t1), e2 = v3(t2);
+    V3 pvec = cross(ray.d, e2);
+    float det = dot(e1, pvec);
+    if (fabsf(det) < 1e-8f) return;
+    float inv = __fdividef(1.0f, det);
+    V3 tvec = ray.o - v3(t0);
+    float u = dot(tvec, pvec) * inv;
+    if (u < 0.0f || u > 1.0f) return;
+    V3 qvec = cross(tvec, e1);
+    float v = dot(ray.d, qvec) * inv;
+    if (v < 0.0f || u + v > 1.0f) return;
+    float t = dot(e2, qvec) * inv;
+    if (t < tmin || t > hit.t) return;
+    hit.t = t;
+    hit.prim = prim;
+    hit.u = u;
+    hit.v = v;
+}
+
+template <bool STATS>
+__device__ __forceinline__ void hit_prim(const DevScene& S, uint32_t type, uint32_t idx, const Ray& ray, float inv_a, float tmin,
+                                         uint32_t origin_prim, Hit& hit, Stats* st) {
+    uint32_t prim = (type << 28) | idx;
+    if (type == PT_SPHERE) {
+        if (STATS) st->sphere_tests++;
+        float4 s = ldg4(S.sph + idx);
+        hit_sphere<STATS>(v3(s), s.w, S.sph_d + 4 * (size_t)idx, false, prim == origin_prim, ray, inv_a, tmin, prim, hit, st);
+    } else if (type == PT_QUAD) {
+        if (STATS) st->quad_tests++;
+        if (prim == origin_prim) return;  // a ray leaving a planar primitive cannot hit it again
+        const float4* q = S.quad + 3 * (size_t)idx;
+        hit_quad(ldg4(q), ldg4(q + 1), ldg4(q + 2), ray, tmin, prim, hit);
+    } else if (type == PT_TRI) {
+        if (STATS) st->tri_tests++;
+        if (prim == origin_prim) return;
+        const float4* t = S.tri + 3 * (size_t)idx;
+        hit_tri(ldg4(t), ldg4(t + 1), ldg4(t + 2), ray, tmin, prim, hit);
+    } else {
+        if (STATS) st->sphere_tests++;
+        const float4* m = S.msph + 2 * (size_t)idx;
+        float4 a = ldg4(m), b = ldg4(m + 1);
+        V3 c = fma3(ray.time, v3(b), v3(a));  // sphere.h:33 center.at(r.time())
+        hit_sphere<STATS>(c, a.w, S.msph_d + 8 * (size_t)idx, true, prim == origin_prim, ray, inv_a, tmin, prim, hit, st);
+    }
+}
+
+// bvh.h:64-72 + aabb.h:61-85 + hittable_list.h:22-35, as an iterative stack traversal of the
+// flattened SAH tree: closest hit over (tmin, tmax).
+template <bool STATS>
+__device__ __forceinline__ void traverse(const DevScene& S, const Ray& ray, float tmin, float tmax, uint32_t origin_prim,
+                                         Hit& hit, Stats* st, int* overflow) {
+    hit.t = tmax;
+    hit.prim = PRIM_NONE;
+    hit.u = hit.v = 0.0f;
+    auto safe_inv = [](float d) { return 1.0f / (fabsf(d) > 1e-30f ? d : copysignf(1e-30f, d)); };
+    const float idx = safe_inv(ray.d.x), idy = safe_inv(ray.d.y), idz = safe_inv(ray.d.z);
+    const float ox = ray.o.x * idx, oy = ray.o.y * idy, oz = ray.o.z * idz;
+    const float inv_a = 1.0f / dot(ray.d, ray.d);
+    if (STATS) st->rays++;
+
+    int stack_link[STACK_SIZE];
+    float stack_t[STACK_SIZE];
+    int sp = 0;
+    int cur = S.root;
+    while (true) {
+        if (cur >= 0) {
+            const float4* n = S.nodes + 4 * (size_t)cur;
+            float4 a = ldg4(n), b = ldg4(n + 1), c = ldg4(n + 2), e = ldg4(n + 3);
+            if (STATS) { st->node_visits++; st->box_tests += 2; }
+            float lx0 = fmaf(a.x, idx, -ox), lx1 = fmaf(b.x, idx, -ox);
+            float ly0 = fmaf(a.y, idy, -oy), ly1 = fmaf(b.y, idy, -oy);
+            float lz0 = fmaf(a.z, idz, -oz), lz1 = fmaf(b.z, idz, -oz);
+            float ln = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), tmin));
+            float lf = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), hit.t));
+            float rx0 = fmaf(c.x, idx, -ox), rx1 = fmaf(e.x, idx, -ox);
+            float ry0 = fmaf(c.y, idy, -oy), ry1 = fmaf(e.y, idy, -oy);
+            float rz0 = fmaf(c.z, idz, -oz), rz1 = fmaf(e.z, idz, -oz);
+            float rn = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), tmin));
+            float rf = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), hit.t));
+            bool hl = ln <= lf, hr = rn <= rf;
+            int linkl = __float_as_int(a.w), linkr = __float_as_int(b.w);
+            if (hl && hr) {
+                bool swap = rn < ln;
+                int near_l = swap ? linkr : linkl, far_l = swap ? linkl : linkr;
+                float far_t = swap ? ln : rn;
+                if (sp < STACK_SIZE) {
+                    stack_link[sp] = far_l;
+                    stack_t[sp] = far_t;
+                    sp++;
+                } else {
+                    *overflow = 1;
+                }
+                cur = near_l;
+                continue;
+            } else if (hl) {
+                cur = linkl;
+                continue;
+            } else if (hr) {
+                cur = linkr;
+                continue;
+            }
+        } else {
+            uint32_t v = ~(uint32_t)cur;
+            uint32_t type = v >> 28, cnt = ((v >> 25) & 7u) + 1u, first = v & 0x1ffffffu;
+            for (uint32_t i = 0; i < cnt; i++) hit_prim<STATS>(S, type, first + i, ray, inv_a, tmin, origin_prim, hit, st);
+        }
+        // pop, skipping subtrees that start beyond the closest hit so far
+        bool found = false;
+        while (sp > 0) {
+            sp--;
+            if (stack_t[sp] <= hit.t) {
+                cur = stack_link[sp];
+                found = true;
+                break;
+            }
+        }
+        if (!found) break;
+    }
+}
+
+// Closest hit of `ray` over (lo, hi) against a medium's boundary primitives (no BVH:
+// a boundary is one sphere or the six quads of a box in every scene of the reference).
+template <bool STATS>
+__device__ __forceinline__ float boundary_hit(const DevScene& S, const DevMedium& m, const Ray& ray, float inv_a, float lo,
+                                              float hi, Stats* st) {
+    Hit h;
+    h.t = hi;
+    h.prim = PRIM_NONE;
+    h.u = h.v = 0.0f;
+    for (int i = 0; i < m.bcount; i++) {
+        uint32_t ref = __ldg(S.boundary + m.bfirst + i);
+        if (STATS) st->boundary_tests++;
+        hit_prim<false>(S, ref >> 28, ref & 0x0fffffffu, ray, inv_a, lo, PRIM_NONE, h, st);
+    }
+    return h.prim == PRIM_NONE ? __int_as_float(0x7fc00000) : h.t;  // NaN = miss
+}
+
+// constant_medium.h:20-53 for every medium, against the closest surface hit so far.
+// Returns the index of the medium that scattered the ray (or -1) and updates t_hit.
+template <bool STATS>
+__device__ __forceinline__ int media_hit(const DevScene& S, const Ray& ray, float tmin, float& t_hit, const Rng& rng,
+                                         uint32_t bounce, Stats* st) {
+    int which = -1;
+    const float inv_a = 1.0f / dot(ray.d, ray.d);
+    const float ray_length = sqrtf(dot(ray.d, ray.d));
+    float4 u4 = make_float4(0, 0, 0, 0);
+    for (int m = 0; m < S.n_media; m++) {
+        if ((m & 3) == 0) u4 = rng.draw(bounce, RS_MEDIUM + (m >> 2));
+        float u = (m & 3) == 0 ? u4.x : ((m & 3) == 1 ? u4.y : ((m & 3) == 2 ? u4.z : u4.w));
+        const DevMedium& md = S.media[m];
+        if (STATS) st->medium_queries++;
+        const float inf = __int_as_float(0x7f800000);
+        float t1 = boundary_hit<STATS>(S, md, ray, inv_a, -inf, inf, st);  // interval::universe
+        if (!(t1 == t1)) continue;
+        float t2 = boundary_hit<STATS>(S, md, ray, inv_a, t1 + 0.0001f, inf, st);
+        if (!(t2 == t2)) continue;
+        if (t1 < tmin) t1 = tmin;
+        if (t2 > t_hit) t2 = t_hit;
+        if (t1 >= t2) continue;
+        if (t1 < 0.0f) t1 = 0.0f;
+        float distance_inside = (t2 - t1) * ray_length;
+        float hit_distance = md.neg_inv_density * logf(u);
+        if (hit_distance > distance_inside) continue;
+        t_hit = t1 + hit_distance / ray_length;
+        which = m;
+    }
+    return which;
+}
+
+// ---------------------------------------------------------------------------------
+// textures (texture.h) and Perlin noise (perlin.h)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float perlin_noise(const DevScene& S, int pidx, double px, double py, double pz) {
+    const float4* vec = S.perlin_vec + 256 * (size_t)pidx;
+    const unsigned char* perm = S.perlin_perm + 768 * (size_t)pidx;
+    // the lattice split is done in double: 2^6 * p reaches ~1e5 in the book-2 scene, where an
+    // FP32 fractional part would have only ~8 good bits
+    double fx = floor(px), fy = floor(py), fz = floor(pz);
+    float u = (float)(px - fx), v = (float)(py - fy), w = (float)(pz - fz);
+    int i = (int)fx, j = (int)fy, k = (int)fz;
+    float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+    float accum = 0.0f;
+#pragma unroll
+    for (int di = 0; di < 2; di++)
+#pragma unroll
+        for (int dj = 0; dj < 2; dj++)
+#pragma unroll
+            for (int dk = 0; dk < 2; dk++) {
+                int h = __ldg(perm + ((i + di) & 255)) ^ __ldg(perm + 256 + ((j + dj) & 255)) ^ __ldg(perm + 512 + ((k + dk) & 255));
+                float4 g = ldg4(vec + h);
+                float wx = u - di, wy = v - dj, wz = w - dk;
+                accum += (di ? uu : 1.0f - uu) * (dj ? vv : 1.0f - vv) * (dk ? ww : 1.0f - ww) * (g.x * wx + g.y * wy + g.z * wz);
+            }
+    return accum;
+}
+
+__device__ __forceinline__ float perlin_turb(const DevScene& S, int pidx, V3 p, int depth) {
+    float accum = 0.0f, weight = 1.0f;
+    double x = p.x, y = p.y, z = p.z;
+    for (int i = 0; i < depth; i++) {
+        accum += weight * perlin_noise(S, pidx, x, y, z);
+        weight *= 0.5f;
+        x *= 2.0; y *= 2.0; z *= 2.0;
+    }
+    return fabsf(accum);
+}
+
+__device__ __forceinline__ V3 tex_value(const DevScene& S, int tex, float u, float v, V3 p) {
+    // checker textures select a child and recurse (texture.h:42-50, 66-76): iterate instead
+    for (int level = 0; level < 16; level++) {
+        const DevTexture& t = S.texs[tex];
+        if (t.type == RT_TEX_SOLID) {
+            return v3(t.color);
+        } else if (t.type == RT_TEX_CHECKER) {
+            int xi = (int)floorf(t.scale * p.x), yi = (int)floorf(t.scale * p.y), zi = (int)floorf(t.scale * p.z);
+            tex = ((xi + yi + zi) % 2 == 0) ? t.a : t.b;
+        } else if (t.type == RT_TEX_CHECKER_TRIANGLE) {
+            v = 1.0f - v;  // texture.h:68: flipped, and the flipped value is what the child sees
+            int ui = (int)roundf(t.scale * u * 10.0f), vi = (int)roundf(t.scale * v * 10.0f);
+            tex = ((ui + vi) % 2 == 0) ? t.a : t.b;
+        } else if (t.type == RT_TEX_IMAGE) {
+            if (t.a < 0) return v3(0.0f, 1.0f, 1.0f);  // texture.h:92
+            const DevImage& im = S.images[t.a];
+            float uc = fminf(fmaxf(u, 0.0f), 1.0f);
+            float vc = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
+            int i = (int)(uc * im.w), j = (int)(vc * im.h);
+            i = i < 0 ? 0 : (i < im.w ? i : im.w - 1);  // rtw_stb_image.h:83-88
+            j = j < 0 ? 0 : (j < im.h ? j : im.h - 1);
+            const unsigned char* px = im.rgb + 3 * ((size_t)j * im.w + i);
+            const float s = 1.0f / 255.0f;
+            return v3(s * __ldg(px), s * __ldg(px + 1), s * __ldg(px + 2));
+        } else {  // noise: texture.h:115
+            float turb = perlin_turb(S, t.a, p, 7);
+            float val = 0.5f * (1.0f + sinf(fmaf(t.scale, p.z, 10.0f * turb)));
+            return v3(val, val, val);
+        }
+    }
+    return v3(0, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------
+// hit record completion + materials (material.h)
+// ---------------------------------------------------------------------------------
+struct Surface {
+    V3 p, normal;
+    float u, v;
+    int material;
+    int prim_id;
+    bool front;
+};
+
+__device__ __forceinline__ void sphere_uv(V3 n, float& u, float& v) {  // sphere.h:67-73
+    const float pi = 3.14159265358979323846f;
+    float theta = acosf(fminf(fmaxf(-n.y, -1.0f), 1.0f));
+    float phi = atan2f(-n.z, n.x) + pi;
+    u = phi / (2.0f * pi);
+    v = theta / pi;
+}
+
+__device__ __forceinline__ void complete_hit(const DevScene& S, const Ray& ray, const Hit& hit, Surface& sf, bool want_uv) {
+    uint32_t type = hit.prim >> 28, idx = hit.prim & 0x0fffffffu;
+    sf.p = fma3(hit.t, ray.d, ray.o);
+    V3 outward;
+    sf.u = hit.u;
+    sf.v = hit.v;
+    if (type == PT_SPHERE || type == PT_MSPHERE) {
+        V3 c;
+        float r;
+        int4 sh;
+        if (type == PT_SPHERE) {
+            float4 s = ldg4(S.sph + idx);
+            c = v3(s); r = s.w;
+            sh = __ldg(S.sph_sh + idx);
+        } else {
+            float4 a = ldg4(S.msph + 2 * (size_t)idx), b = ldg4(S.msph + 2 * (size_t)idx + 1);
+            c = fma3(ray.time, v3(b), v3(a)); r = a.w;
+            sh = __ldg(S.msph_sh + idx);
+        }
+        outward = (1.0f / r) * (sf.p - c);  // sphere.h:52
+        sf.material = sh.x;
+        sf.prim_id = sh.z;
+        sf.u = sf.v = 0.0f;
+        if (want_uv || (sh.x >= 0 && S.mats[sh.x].needs_uv)) {
+            V3 n = outward;
+            if (sh.y >= 0) {  // back to object space: R^T n
+                const float* R = S.xrot + 9 * (size_t)sh.y;
+                n = v3(R[0] * outward.x + R[3] * outward.y + R[6] * outward.z,
+                       R[1] * outward.x + R[4] * outward.y + R[7] * outward.z,
+                       R[2] * outward.x + R[5] * outward.y + R[8] * outward.z);
+            }
+            sphere_uv(n, sf.u, sf.v);
+        }
+    } else if (type == PT_QUAD) {
+        outward = v3(ldg4(S.quad + 3 * (size_t)idx));
+        int4 sh = __ldg(S.quad_sh + idx);
+        sf.material = sh.x;
+        sf.prim_id = sh.z;
+    } else {
+        const float4* ts = S.tri_sh + 3 * (size_t)idx;
+        float4 a = ldg4(ts), b = ldg4(ts + 1), c = ldg4(ts + 2);
+        outward = v3(a);
+        sf.material = __float_as_int(a.w);
+        sf.prim_id = __float_as_int(c.z);
+        float alpha = 1.0f - hit.u - hit.v, beta = hit.u, gamma = hit.v;  // triangle.h:96-104
+        sf.u = alpha * b.x + beta * b.z + gamma * c.x;
+        sf.v = alpha * b.y + beta * b.w + gamma * c.y;
+    }
+    sf.front = dot(ray.d, outward) < 0.0f;  // hittable.h:22-25
+    sf.normal = sf.front ? outward : -outward;
+}
+
+// vec3.h:107-115: the `1e-160 < lensq <= 1` test is always true, so this is
+// normalise(uniform point of the cube [-1,1]^3) with no rejection.
+__device__ __forceinline__ V3 random_unit_vector(float ux, float uy, float uz) {
+    V3 p = v3(fmaf(2.0f, ux, -1.0f), fmaf(2.0f, uy, -1.0f), fmaf(2.0f, uz, -1.0f));
+    float lensq = dot(p, p);
+    return (1.0f / sqrtf(lensq)) * p;
+}
+__device__ __forceinline__ V3 reflect(V3 v, V3 n) { return v - 2.0f * dot(v, n) * n; }
+__device__ __forceinline__ bool near_zero(V3 v) { return fabsf(v.x) < 1e-8f && fabsf(v.y) < 1e-8f && fabsf(v.z) < 1e-8f; }
+
+// material::emitted (material.h:14,99-101,111-113)
+__device__ __forceinline__ V3 mat_emitted(const DevScene& S, const DevMaterial& m, const Surface& sf) {
+    if (m.type == RT_MAT_DIFFUSE_LIGHT || m.type == RT_MAT_EMISSIVE_LIGHT) return tex_value(S, m.tex, sf.u, sf.v, sf.p);
+    return v3(0, 0, 0);
+}
+
+// material::scatter (material.h:29-38, 47-74, 82-88, 129-134, 145-167).  `u4` holds the
+// uniforms of this bounce (see Rng).  Returns false when the ray is absorbed.
+__device__ __forceinline__ bool mat_scatter(const DevScene& S, const DevMaterial& m, const Ray& in, const Surface& sf, float4 u4,
+                                            V3& attenuation, Ray& out) {
+    out.o = sf.p;
+    out.time = in.time;
+    switch (m.type) {
+        case RT_MAT_LAMBERTIAN: {
+            V3 dir = sf.normal + random_unit_vector(u4.x, u4.y, u4.z);
+            if (near_zero(dir)) dir = sf.normal;
+            out.d = dir;
+            attenuation = tex_value(S, m.tex, sf.u, sf.v, sf.p);
+            return true;
+        }
+        case RT_MAT_METAL: {
+            V3 refl = reflect(in.d, sf.normal);
+            refl = normalize(refl) + m.param * random_unit_vector(u4.x, u4.y, u4.z);
+            out.d = refl;
+            attenuation = v3(m.albedo);
+            return dot(refl, sf.normal) > 0.0f;
+        }
+        case RT_MAT_DIELECTRIC: {
+            attenuation = v3(1.0f, 1.0f, 1.0f);
+            float ri = sf.front ? (1.0f / m.param) : m.param;
+            V3 unit = normalize(in.d);
+            float cos_theta = fminf(dot(-unit, sf.normal), 1.0f);
+            float sin_theta = sqrtf(fmaxf(1.0f - cos_theta * cos_theta, 0.0f));
+            bool cannot_refract = ri * sin_theta > 1.0f;
+            float r0 = (1.0f - ri) / (1.0f + ri);
+            r0 = r0 * r0;
+            float x = 1.0f - cos_theta;
+            float reflectance = r0 + (1.0f - r0) * (x * x) * (x * x) * x;
+            if (cannot_refract || reflectance > u4.w) {
+                out.d = reflect(unit, sf.normal);
+            } else {  // vec3.h:128-133
+                V3 perp = ri * (unit + cos_theta * sf.normal);
+                V3 para = -sqrtf(fabsf(1.0f - dot(perp, perp))) * sf.normal;
+                out.d = perp + para;
+            }
+            return true;
+        }
+        case RT_MAT_ISOTROPIC: {
+            out.d = random_unit_vector(u4.x, u4.y, u4.z);
+            attenuation = tex_value(S, m.tex, sf.u, sf.v, sf.p);
+            return true;
+        }
+        case RT_MAT_SPECULAR: {
+            V3 unit = normalize(in.d);
+            V3 refl = reflect(unit, sf.normal);
+            V3 diffuse = random_unit_vector(u4.x, u4.y, u4.z);  // random_on_hemisphere (vec3.h:116-124)
+            if (!(dot(diffuse, sf.normal) > 0.0f)) diffuse = -diffuse;
+            float factor = powf(1.0f - dot(refl, unit), m.param);
+            V3 dir = factor * refl + (1.0f - factor) * diffuse;
+            if (near_zero(dir)) dir = sf.normal;
+            out.d = dir;
+            attenuation = v3(m.albedo);
+            return true;
+        }
+        default:
+            return false;  // diffuse_light / emissive_light: material.h:17-19, 116-118
+    }
+}
+
+// Camera.txt:240-272: unshadowed point lights
+__device__ __forceinline__ V3 point_lighting(const DevScene& S, V3 p, V3 normal) {
+    V3 result = v3(0, 0, 0);
+    for (int i = 0; i < S.n_lights; i++) {
+        const DevLight& l = S.lights[i];
+        V3 ld = v3(l.pos) - p;
+        float d2 = dot(ld, ld);
+        ld = (1.0f / sqrtf(d2)) * ld;
+        float diffuse = fmaxf(dot(normal, ld), 0.0f);
+        if (d2 <= l.size * l.size) {
+            result = result + diffuse * v3(l.intensity);
+        } else {
+            float att = 1.0f / (d2 + l.size * 0.1f);
+            result = result + (diffuse * att) * v3(l.intensity);
+        }
+    }
+    return result;
+}
+
+// Camera.txt:177-200 get_ray.  Directions are built relative to the camera centre
+// (dir00 = pixel00_loc - center, evaluated in double on the host) so that FP32 keeps
+// sub-pixel accuracy when the camera sits hundreds of units from the origin.
+__device__ __forceinline__ Ray camera_ray(const DevScene& S, int i, int j, const Rng& rng) {
+    float4 u = rng.draw(0, RS_CAMERA);
+    float fx = (float)i + (u.x - 0.5f), fy = (float)j + (u.y - 0.5f);
+    V3 dir = fma3(fx, v3(S.du), fma3(fy, v3(S.dv), v3(S.dir00)));
+    Ray r;
+    r.o = v3(S.center);
+    r.time = u.z;
+    if (S.defocus) {
+        // random_in_unit_disk (vec3.h:135-142): rejection sampling, two candidates per draw
+        float px = 0.0f, py = 0.0f;
+        for (uint32_t attempt = 0;; attempt++) {
+            float4 c = rng.draw(0, RS_DEFOCUS + (attempt < 14 ? attempt : 14));
+            px = fmaf(2.0f, c.x, -1.0f); py = fmaf(2.0f, c.y, -1.0f);
+            if (px * px + py * py < 1.0f) break;
+            px = fmaf(2.0f, c.z, -1.0f); py = fmaf(2.0f, c.w, -1.0f);
+            if (px * px + py * py < 1.0f) break;
+            if (attempt >= 14) { px = py = 0.0f; break; }  // (1 - pi/4)^30 ~ 1e-20
+        }
+        V3 off = fma3(px, v3(S.disk_u), py * v3(S.disk_v));
+        r.o = r.o + off;
+        dir = dir - off;
+    }
+    r.d = dir;
+    return r;
+}
+
+}  // namespace rtdev

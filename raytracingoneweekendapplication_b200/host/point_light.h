@@ -1,0 +1,4 @@
+// point_light.h — forwarding header: the reference's `#include "point_light.h"` resolves to the
+// host-side mirror of its scene API (see rtow_host.h).
+#pragma once
+#include "rtow_host.h"

@@ -1,0 +1,4 @@
+// texture.h — forwarding header: the reference's `#include "texture.h"` resolves to the
+// host-side mirror of its scene API (see rtow_host.h).
+#pragma once
+#include "rtow_host.h"

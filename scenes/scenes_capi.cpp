@@ -1,0 +1,73 @@
+// scenes_capi.cpp — builds the BASELINE scenes (scenes.h) against the host mirror of the
+// reference's scene API and hands the flattened description to callers that are not C++
+// (the pytest suite and bench.py, via ctypes).  Links against librt_b200.so because the
+// mirror's camera::render calls the C ABI.
+#include "rtow_host.h"
+
+#include "scenes.h"
+
+struct rtsc_scene {
+    rtb200::flat_scene fs;
+    rt_scene_desc desc;
+    scene_config cfg;
+    int max_depth;
+};
+
+extern "C" {
+
+int rtsc_scene_count() {
+    int n = 0;
+    scene_names(&n);
+    return n;
+}
+const char* rtsc_scene_name(int i) {
+    int n = 0;
+    const char* const* names = scene_names(&n);
+    return (i >= 0 && i < n) ? names[i] : nullptr;
+}
+
+// Builds scene `name` with construction seed `seed`; returns NULL for an unknown name.
+rtsc_scene* rtsc_build(const char* name, unsigned seed, const char* asset_dir) {
+    rtsc_scene* s = new rtsc_scene();
+    if (asset_dir) s->cfg.asset_dir = asset_dir;
+    hittable_list world;
+    camera cam;
+    std::vector<point_light> lights;
+    if (!build_scene(name, seed, world, cam, lights, s->cfg)) {
+        delete s;
+        return nullptr;
+    }
+    rtb200::flatten_scene(world, lights, s->fs);
+    cam.export_camera(s->fs.camera);
+    s->desc = s->fs.desc();
+    s->max_depth = cam.max_depth;
+    return s;
+}
+const rt_scene_desc* rtsc_desc(const rtsc_scene* s) { return s ? &s->desc : nullptr; }
+void rtsc_frame(const rtsc_scene* s, int* width, int* height, int* spp, int* depth) {
+    if (width) *width = s->cfg.width;
+    if (height) *height = s->cfg.height;
+    if (spp) *spp = s->cfg.spp;
+    if (depth) *depth = s->cfg.depth;
+}
+void rtsc_free(rtsc_scene* s) { delete s; }
+
+// The whole reference-facing path in one call: build the scene with the mirror API and
+// run camera::render (flatten -> rt_upload_scene -> rt_render -> rt_download -> PNG).
+int rtsc_render_png(const char* name, unsigned seed, const char* asset_dir, int width, int height, int spp, int depth,
+                    const char* out_png) {
+    scene_config cfg;
+    if (asset_dir) cfg.asset_dir = asset_dir;
+    hittable_list world;
+    camera cam;
+    std::vector<point_light> lights;
+    if (!build_scene(name, seed, world, cam, lights, cfg)) return 1;
+    if (width > 0 && height > 0) { cam.image_width = width; cam.aspect_ratio = double(width) / double(height); }
+    if (spp > 0) cam.samples_per_pixel = spp;
+    if (depth > 0) cam.max_depth = depth;
+    cam.image_name = out_png;
+    cam.render(world, lights);
+    return 0;
+}
+
+}  // extern "C"
