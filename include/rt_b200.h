@@ -304,6 +304,13 @@ int rt_bind_accum(rt_ctx* ctx, void* device_ptr, size_t bytes, int32_t width, in
 
 int rt_get_stats(rt_ctx* ctx, rt_stats* out);
 
+/* sizeof() of the ABI structs as this library was compiled, so that a foreign-language
+ * binding (ctypes, cgo, JNI ...) can verify its own declarations at load time.
+ * which: 0 rt_scene_desc, 1 rt_render_params, 2 rt_stats, 3 rt_sphere, 4 rt_quad,
+ * 5 rt_triangle, 6 rt_medium, 7 rt_material, 8 rt_texture, 9 rt_image, 10 rt_perlin,
+ * 11 rt_point_light, 12 rt_camera, 13 rt_xform, 14 rt_prim_ref; 0 for anything else. */
+size_t rt_struct_size(int which);
+
 /* FP32 FMA issue-rate microbenchmark on the context's device, for the FP32
  * roofline denominator (not in MEASURED_PEAKS.json).  Returns TFLOP/s. */
 int rt_measure_fp32_peak(rt_ctx* ctx, double* tflops);

@@ -292,7 +292,7 @@ int main(int argc, char** argv) {
         sc.cam.initialize();
         if (sc.cam.image_height != H) std::fprintf(stderr, "note: reference height %d != requested %d\n", sc.cam.image_height, H);
         H = sc.cam.image_height;
-        std::vector<float> img((size_t)W * H * 3);
+        std::vector<float> img((size_t)W * H * 3), var((size_t)W * H * 3);
         std::atomic<int> next_row{0};
         auto t0 = std::chrono::steady_clock::now();
         auto worker = [&]() {
@@ -300,12 +300,19 @@ int main(int argc, char** argv) {
                 int j = next_row.fetch_add(1);
                 if (j >= H) break;
                 for (int i = 0; i < W; i++) {
-                    color acc(0, 0, 0);
+                    color acc(0, 0, 0), acc2(0, 0, 0);
                     for (int s = 0; s < spp; s++) {
                         ray r = sc.cam.get_ray(i, j);
-                        acc += sc.cam.ray_color(r, depth, sc.world, sc.lights);
+                        color c = sc.cam.ray_color(r, depth, sc.world, sc.lights);
+                        acc += c;
+                        acc2 += c * c;
                     }
-                    for (int k = 0; k < 3; k++) img[((size_t)j * W + i) * 3 + k] = (float)(acc[k] / spp);
+                    for (int k = 0; k < 3; k++) {
+                        double mean = acc[k] / spp;
+                        img[((size_t)j * W + i) * 3 + k] = (float)mean;
+                        // variance of ONE sample (for the Monte Carlo error bars of the parity tests)
+                        var[((size_t)j * W + i) * 3 + k] = (float)std::max(0.0, acc2[k] / spp - mean * mean);
+                    }
                 }
             }
         };
@@ -314,6 +321,7 @@ int main(int argc, char** argv) {
         for (auto& t : pool) t.join();
         double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         dump(argv[9], img);
+        dump(std::string(argv[9]) + ".var", var);
         std::printf("{\"scene\": \"%s\", \"width\": %d, \"height\": %d, \"spp\": %d, \"seconds\": %.3f, \"threads\": %d}\n",
                     name.c_str(), W, H, spp, s, threads);
         return 0;

@@ -125,8 +125,11 @@ class rt_stats(C.Structure):
 EXPORTED_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_upload_scene", "rt_render", "rt_sync", "rt_download", "rt_render_aov",
     "rt_accum_buffer", "rt_bind_accum", "rt_get_stats", "rt_measure_fp32_peak", "rt_probe_texture", "rt_probe_scatter",
-    "rt_probe_hit",
+    "rt_probe_hit", "rt_struct_size",
 ]
+
+ABI_STRUCTS = [rt_scene_desc, rt_render_params, rt_stats, rt_sphere, rt_quad, rt_triangle, rt_medium, rt_material, rt_texture,
+               rt_image, rt_perlin, rt_point_light, rt_camera, rt_xform, rt_prim_ref]
 
 _lib = None
 _scenes = None
@@ -174,6 +177,12 @@ def load() -> C.CDLL:
     lib.rt_probe_texture.argtypes = [vp, i32, i32, vp, vp]
     lib.rt_probe_scatter.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.rt_probe_hit.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.rt_struct_size.argtypes = [C.c_int]
+    lib.rt_struct_size.restype = C.c_size_t
+    for which, struct in enumerate(ABI_STRUCTS):
+        if lib.rt_struct_size(which) != C.sizeof(struct):
+            raise ImportError(f"ABI mismatch: {struct.__name__} is {C.sizeof(struct)} bytes here, "
+                              f"{lib.rt_struct_size(which)} in {path}")
     _lib = lib
     return lib
 

@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Dev
         const uint32_t pixel = (uint32_t)(py * A.width + px);
 
         int s = (int)seg * A.seg_len;
-        const int s_end = inside ? min(s + A.seg_len, A.n_local_samples) : s;
+        // ray_color(depth <= 0) is black before anything is traced (Camera.txt:205-206)
+        const int s_end = (inside && A.max_depth > 0) ? min(s + A.seg_len, A.n_local_samples) : s;
 
         unsigned long long sum_r = 0, sum_g = 0, sum_b = 0;
         Rng rng;
@@ -203,7 +204,7 @@ __global__ void aov_kernel(const __grid_constant__ DevScene S, int width, int he
     float t = 0.0f;
     if (hit.prim != PRIM_NONE) {
         complete_hit(S, ray, hit, sf, true);
-        t = hit.t;
+        t = sf.t;
     }
     if (prim_id) prim_id[px] = sf.prim_id;
     if (t_out) t_out[px] = t;
@@ -279,9 +280,10 @@ __global__ void probe_hit_kernel(const __grid_constant__ DevScene S, int n, cons
     sf.prim_id = -1;
     sf.normal = v3(0, 0, 0);
     sf.u = sf.v = 0;
+    sf.t = 0.0f;
     if (hit.prim != PRIM_NONE) complete_hit(S, ray, hit, sf, true);
     if (prim_id) prim_id[i] = sf.prim_id;
-    if (t_out) t_out[i] = hit.prim != PRIM_NONE ? hit.t : 0.0f;
+    if (t_out) t_out[i] = sf.t;
     if (normal) { normal[3 * i] = sf.normal.x; normal[3 * i + 1] = sf.normal.y; normal[3 * i + 2] = sf.normal.z; }
     if (uv) { uv[2 * i] = sf.u; uv[2 * i + 1] = sf.v; }
 }
@@ -1039,6 +1041,13 @@ extern "C" int rt_get_stats(rt_ctx* ctx, rt_stats* out) {
     if (!ctx || !out) return RT_ERR_INVALID;
     *out = ctx->stats;
     return RT_OK;
+}
+
+extern "C" size_t rt_struct_size(int which) {
+    static const size_t sizes[] = {sizeof(rt_scene_desc), sizeof(rt_render_params), sizeof(rt_stats), sizeof(rt_sphere), sizeof(rt_quad),
+                                   sizeof(rt_triangle), sizeof(rt_medium), sizeof(rt_material), sizeof(rt_texture), sizeof(rt_image),
+                                   sizeof(rt_perlin), sizeof(rt_point_light), sizeof(rt_camera), sizeof(rt_xform), sizeof(rt_prim_ref)};
+    return (which >= 0 && which < (int)(sizeof(sizes) / sizeof(sizes[0]))) ? sizes[which] : 0;
 }
 
 extern "C" int rt_measure_fp32_peak(rt_ctx* ctx, double* tflops) {

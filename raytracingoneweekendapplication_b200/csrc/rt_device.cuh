@@ -485,6 +485,7 @@ __device__ __forceinline__ V3 tex_value(const DevScene& S, int tex, float u, flo
 // hit record completion + materials (material.h)
 // ---------------------------------------------------------------------------------
 struct Surface {
+    float t;
     V3 p, normal;
     float u, v;
     int material;
@@ -502,24 +503,42 @@ __device__ __forceinline__ void sphere_uv(V3 n, float& u, float& v) {  // sphere
 
 __device__ __forceinline__ void complete_hit(const DevScene& S, const Ray& ray, const Hit& hit, Surface& sf, bool want_uv) {
     uint32_t type = hit.prim >> 28, idx = hit.prim & 0x0fffffffu;
+    sf.t = hit.t;
     sf.p = fma3(hit.t, ray.d, ray.o);
     V3 outward;
     sf.u = hit.u;
     sf.v = hit.v;
     if (type == PT_SPHERE || type == PT_MSPHERE) {
-        V3 c;
-        float r;
+        // The accepted sphere hit is re-solved ONCE in double (sphere.h:33-52 verbatim): the
+        // FP32 traversal fixes WHICH root of WHICH sphere, the FP64 pass fixes t, p and the
+        // normal, so that a far-away small sphere still gets a normal good to FP32 rounding.
         int4 sh;
+        double cx, cy, cz, rr;
         if (type == PT_SPHERE) {
-            float4 s = ldg4(S.sph + idx);
-            c = v3(s); r = s.w;
+            const double* cd = S.sph_d + 4 * (size_t)idx;
+            cx = cd[0]; cy = cd[1]; cz = cd[2]; rr = cd[3];
             sh = __ldg(S.sph_sh + idx);
         } else {
-            float4 a = ldg4(S.msph + 2 * (size_t)idx), b = ldg4(S.msph + 2 * (size_t)idx + 1);
-            c = fma3(ray.time, v3(b), v3(a)); r = a.w;
+            const double* cd = S.msph_d + 8 * (size_t)idx;
+            cx = cd[0] + (double)ray.time * cd[4]; cy = cd[1] + (double)ray.time * cd[5]; cz = cd[2] + (double)ray.time * cd[6];
+            rr = cd[3];
             sh = __ldg(S.msph_sh + idx);
         }
-        outward = (1.0f / r) * (sf.p - c);  // sphere.h:52
+        {
+            double ox = cx - (double)ray.o.x, oy = cy - (double)ray.o.y, oz = cz - (double)ray.o.z;
+            double dx = ray.d.x, dy = ray.d.y, dz = ray.d.z;
+            double a = dx * dx + dy * dy + dz * dz;
+            double hh = dx * ox + dy * oy + dz * oz;
+            double cc = ox * ox + oy * oy + oz * oz - rr * rr;
+            double sq = sqrt(fmax(hh * hh - a * cc, 0.0));
+            double ta = (hh - sq) / a, tb = (hh + sq) / a;
+            double td = fabs(ta - (double)hit.t) <= fabs(tb - (double)hit.t) ? ta : tb;
+            double px = (double)ray.o.x + td * dx, py = (double)ray.o.y + td * dy, pz = (double)ray.o.z + td * dz;
+            double inv_r = 1.0 / rr;
+            sf.t = (float)td;
+            sf.p = v3((float)px, (float)py, (float)pz);
+            outward = v3((float)((px - cx) * inv_r), (float)((py - cy) * inv_r), (float)((pz - cz) * inv_r));  // sphere.h:52
+        }
         sf.material = sh.x;
         sf.prim_id = sh.z;
         sf.u = sf.v = 0.0f;

@@ -79,7 +79,7 @@ class vec3 {
     // argument evaluation order is unspecified in C++ and g++ (the compiler the oracle is
     // built with) evaluates right to left, so the FIRST draw lands in z.  Sequenced
     // explicitly here so that scenes and Perlin tables match the oracle's
-    // (checked by tests/test_scenes.py against oracle/_ref).
+    // (checked by tests/test_scenes.py against the compiled reference).
     static vec3 random() {
         double c = random_double(), b = random_double(), a = random_double();
         return vec3(a, b, c);

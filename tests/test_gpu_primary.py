@@ -1,0 +1,95 @@
+"""Parity gate (a): deterministic primary rays at pixel centres.  The device's hit primitive
+must equal the reference's on >= 99.99 % of pixels, with t and normal within 1e-5 relative
+(FP32 device vs the reference's double).  All calls go through the C ABI (rt_render_aov /
+rt_probe_hit)."""
+import numpy as np
+import pytest
+
+import fuzz_scenes
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+SCENES = ["book1", "cornell", "cornell_smoke", "mesh", "final", "quads", "emissive", "specular", "mixed", "kitchen_sink"]
+T_TOL = 1e-5   # relative, north_star
+N_TOL = 1e-5   # absolute on unit normals
+
+
+def check(r):
+    assert r["id_match"] >= 0.9999, r
+    assert r["t_within_1e5"] >= 0.9999 and r["t_rel_max"] <= 10 * T_TOL, r
+    assert r["n_within_1e5"] >= 0.9999 and r["n_err_max"] <= 10 * N_TOL, r
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_primary_hits_match_reference_fixture(ctx, scene_of, name):
+    """Against tests/golden/primary_*.npz, dumped from the unmodified reference renderer."""
+    sc = scene_of(name)
+    ctx.upload(sc)
+    g = helpers.golden("primary", name)
+    h, w = g["ids"].shape
+    r = helpers.compare_primary(g, ctx.aov(w, h), helpers.flat_leaf_keys(sc.desc))
+    check(r)
+    assert r["uv_err_max"] <= 2e-4, r
+
+
+@pytest.mark.parametrize("name,w,h", [("book1", 400, 225), ("cornell", 600, 600), ("cornell_smoke", 600, 600),
+                                      ("mesh", 960, 540), ("final", 960, 540)])
+def test_primary_hits_match_oracle_at_baseline_frames(ctx, scene_of, name, w, h):
+    """The BASELINE frame (C4/C5 at half resolution per axis) against the CPU restatement,
+    which is itself pinned bit-exactly to the reference fixtures (test_oracle_port.py)."""
+    from oracle import port
+
+    sc = scene_of(name)
+    ctx.upload(sc)
+    o = port.primary(sc, w, h)
+    keys = helpers.flat_leaf_keys(sc.desc)
+    gold = {"ids": o["prim_id"].reshape(h, w), "t": o["t"].reshape(h, w), "normal": o["normal"].reshape(h, w, 3),
+            "uv": o["uv"].reshape(h, w, 2), "leaves": keys}
+    check(helpers.compare_primary(gold, ctx.aov(w, h), keys))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_rays_random_scenes_match_oracle(ctx, seed):
+    """Fuzz: random spheres (static + moving), quads, triangles under random rotate_y/translate
+    instances; random rays with random times.  rt_probe_hit vs oracle_hit."""
+    from oracle import port
+
+    sc = fuzz_scenes.random_scene(seed)
+    ctx.upload(sc)
+    rays = fuzz_scenes.random_rays(100 + seed, 20000)
+    dev = ctx.probe_hit(rays)
+    ref = port.hit(sc, rays)
+    same = dev["prim_id"] == ref["prim_id"]
+    tie = (~same) & (dev["prim_id"] >= 0) & (ref["prim_id"] >= 0) & (np.abs(dev["t"] - ref["t"]) <= 2e-6 * np.abs(ref["t"]))
+    assert (same | tie).mean() >= 0.9995, ((~(same | tie)).sum(), len(same))
+    both = same & (ref["prim_id"] >= 0)
+    assert both.sum() > 5000
+    rel = np.abs(dev["t"][both] - ref["t"][both]) / np.abs(ref["t"][both])
+    assert np.quantile(rel, 0.999) <= T_TOL and rel.max() <= 1e-3, (np.quantile(rel, 0.999), rel.max())
+    nerr = np.abs(dev["normal"][both] - ref["normal"][both]).max(axis=1)
+    assert np.quantile(nerr, 0.999) <= N_TOL, np.quantile(nerr, 0.999)
+
+
+def test_empty_and_single_primitive_worlds(ctx):
+    """Edge cases: an empty world (every ray misses) and a one-primitive world (root is a leaf)."""
+    empty = fuzz_scenes.random_scene(5, 0, 0, 0, with_xforms=False)
+    ctx.upload(empty)
+    a = ctx.aov(64, 36)
+    assert (a["prim_id"] == -1).all()
+    ctx.render(64, 36, 4, max_depth=5)
+    img = ctx.download(4)
+    assert np.allclose(img, np.array([0.5, 0.7, 1.0]), atol=1e-6)   # background only (Camera.txt:212-214)
+    one = fuzz_scenes.random_scene(6, 1, 0, 0, with_xforms=False)
+    ctx.upload(one)
+    from oracle import port
+    rays = fuzz_scenes.random_rays(9, 4000)
+    dev, ref = ctx.probe_hit(rays), port.hit(one, rays)
+    assert (dev["prim_id"] == ref["prim_id"]).mean() >= 0.999
+
+
+def test_max_depth_zero_is_black(ctx, scene_of):
+    """ray_color returns black for depth <= 0 before tracing anything (Camera.txt:205-206)."""
+    ctx.upload(scene_of("quads"))
+    ctx.render(32, 32, 2, max_depth=0)
+    assert np.count_nonzero(ctx.download(2)) == 0
