@@ -219,7 +219,13 @@ def run_b200(args):
     ctx.upload(sc)
     accum = torch.zeros(width * height * 4, dtype=torch.int64, device="cuda")
     ctx.bind_accum(accum.data_ptr(), accum.numel() * 8, width, height)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default torch stream: its handle is what rt_render launches on (handle 0, the legacy
+    # default stream, would read as "NULL = the context's own stream" in the C ABI), and the
+    # torch.cuda.Events below are recorded on the same stream
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     plan = sharding.plan(width, height, spp_step, rank, world, sharding.RT_SHARD_AUTO)
     shard = dict(shard_rank=rank, shard_count=world, shard_mode=plan.mode)
 

@@ -271,7 +271,12 @@ class Context:
             raise RtError(rc, self.lib.rt_last_error(self._h).decode())
 
     def upload(self, scene) -> None:
-        ptr = scene.desc_ptr if isinstance(scene, Scene) else (scene if isinstance(scene, C.POINTER(rt_scene_desc)) else C.pointer(scene))
+        if hasattr(scene, "desc_ptr"):          # capi.Scene or any object that keeps a description alive
+            ptr = scene.desc_ptr
+        elif isinstance(scene, rt_scene_desc):
+            ptr = C.pointer(scene)
+        else:
+            ptr = scene
         self._check(self.lib.rt_upload_scene(self._h, ptr))
 
     def render(self, width: int, height: int, spp: int, max_depth: int = 50, seed: int = 1, spp_begin: int = 0,

@@ -38,7 +38,7 @@ PRIMARY = {
 }
 IMAGE = {
     "book1": (120, 68, 4096), "cornell": (64, 64, 32768), "cornell_smoke": (64, 64, 32768), "mesh": (128, 72, 2048),
-    "final": (96, 54, 16384), "quads": (64, 64, 2048), "emissive": (64, 36, 2048), "specular": (96, 54, 4096),
+    "final": (96, 54, 65536), "quads": (64, 64, 2048), "emissive": (64, 36, 2048), "specular": (96, 54, 4096),
     "mixed": (96, 54, 4096), "kitchen_sink": (96, 54, 4096),
 }
 KAT = {"kitchen_sink": 600, "mixed": 400, "final": 400, "book1": 400, "specular": 200, "mesh": 300}

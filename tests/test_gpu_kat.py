@@ -38,11 +38,13 @@ def test_scatter_matches_reference_known_answers(ctx, scene_of, name):
         np.testing.assert_allclose(dev[ok, 1:4], exp[ok, 1:4], rtol=0, atol=att_tol, err_msg=f"attenuation m={m} type={mtype}")
         scale = np.maximum(np.linalg.norm(exp[ok, 7:10], axis=1, keepdims=True), 1e-3)
         derr = np.abs(dev[ok, 7:10] - exp[ok, 7:10]) / scale
-        assert np.quantile(derr, 0.99) <= 2e-5 and derr.max() <= 2e-3, (m, mtype, derr.max())   # scattered direction
+        if derr.size:   # lights never scatter
+            assert np.quantile(derr, 0.99) <= 2e-5 and derr.max() <= 2e-3, (m, mtype, derr.max())   # scattered direction
         np.testing.assert_allclose(dev[:, 10:13], exp[:, 10:13], rtol=1e-6, atol=att_tol, err_msg="emitted")
         # and the fixture itself (reference outputs), loosely: inputs were rounded to FP32
         okr = flag_ok & (ref[:, 22] != 0) & (exp[:, 0] != 0)
-        assert np.quantile(np.abs(dev[okr, 7:10] - ref[okr, 29:32]), 0.95) <= 1e-3
+        if okr.any():
+            assert np.quantile(np.abs(dev[okr, 7:10] - ref[okr, 29:32]), 0.95) <= 1e-3
     assert flagged <= max(1, total // 200), (flagged, total)   # branch flips at |x - u| ~ 1e-7
 
 
