@@ -142,7 +142,8 @@ class RtError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_PKG, "librt_b200.so")
+    # RT_B200_LIB: an alternative build of the same library (tuning experiments, tools/perf_sweep.py)
+    return os.environ.get("RT_B200_LIB") or os.path.join(_PKG, "librt_b200.so")
 
 
 def scenes_lib_path() -> str:

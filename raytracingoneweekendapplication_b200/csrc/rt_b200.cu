@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -183,6 +184,212 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Dev
     }
 }
 
+// ---------------------------------------------------------------------------------
+// render_kernel_v2 — the production megakernel.
+//
+// ncu on the first version (profiles/r1_v1_*.txt) showed 7.8 of 32 threads active per issued
+// instruction: (1) lanes that finished their fixed share of samples idled until the slowest
+// lane of the warp was through, and (2) inside the traversal every lane waited for the
+// longest ray of the warp.  v2 is organised as a per-warp STREAM instead:
+//   * a warp owns no pixels.  It pulls (8x4 pixel block x sample segment) items from a global
+//     counter into a pool of 32 * seg_len (pixel, sample) pairs; an idle lane takes the next
+//     pair of the pool, whatever pixel it belongs to.  Radiance goes to the frame with three
+//     64-bit integer REDs per finished sample, so who traced what does not matter
+//     (order-independent fixed-point sums keep the image bit-identical).
+//   * each lane is a small state machine: IDLE -> TRAVERSE -> SHADE -> TRAVERSE ... -> IDLE.
+//     The warp alternates between a traversal phase, in which lanes step through the BVH
+//     ("while-while": all lanes descend interior nodes until each holds a leaf, then all
+//     intersect their leaf), and a shade phase.  The traversal phase is left as soon as fewer
+//     than kTravThreshold lanes still have a ray in flight; those are suspended with their
+//     stack, the others shade/regenerate, and the next traversal phase runs full again.
+// ---------------------------------------------------------------------------------
+#ifndef RT_TRAV_THRESHOLD
+#define RT_TRAV_THRESHOLD 4
+#endif
+#ifndef RT_MIN_BLOCKS
+#define RT_MIN_BLOCKS 3
+#endif
+#ifndef RT_DESCEND_DIV
+#define RT_DESCEND_DIV 0
+#endif
+constexpr int kTravThreshold = RT_TRAV_THRESHOLD;
+constexpr int kDescendDiv = RT_DESCEND_DIV;
+enum : int { LANE_IDLE = 0, LANE_TRAVERSE = 1, LANE_SHADE = 2 };
+
+template <bool STATS>
+__global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A,
+                                                        unsigned long long* __restrict__ accum,
+                                                        unsigned long long* __restrict__ counters, Stats* __restrict__ gstats) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    Stats st;
+    if (STATS) memset(&st, 0, sizeof st);
+    int overflow = 0;
+
+    // warp-uniform pool of (pixel, sample) pairs
+    unsigned pool_pos = 0, pool_size = 0;
+    int blk_x0 = 0, blk_y0 = 0, seg_s0 = 0;
+    bool exhausted = A.max_depth <= 0;  // ray_color(depth <= 0) is black before anything is traced
+
+    int state = LANE_IDLE;
+    Rng rng;
+    rng.pixel = rng.sample = 0;
+    rng.k0 = A.k0;
+    rng.k1 = A.k1;
+    Ray ray;
+    ray.o = ray.d = v3(0, 0, 0);
+    ray.time = 0;
+    V3 L = v3(0, 0, 0), T = v3(1, 1, 1);
+    uint32_t bounce = 0, origin_prim = PRIM_NONE;
+    Trav tr;
+    StackEntry stack[STACK_SIZE];
+    tr.cur = LINK_DONE;
+    tr.sp = 0;
+    tr.hit.t = 0;
+    tr.hit.prim = PRIM_NONE;
+    tr.hit.u = tr.hit.v = 0;
+    const float kInf = __int_as_float(0x7f800000);
+
+    while (true) {
+        // ---- 1. idle lanes take the next (pixel, sample) pairs of the pool -----------------------
+        unsigned needy = __ballot_sync(0xffffffffu, state == LANE_IDLE);
+        while (needy && !exhausted) {
+            if (pool_pos >= pool_size) {
+                unsigned long long item = 0;
+                if (lane == 0) item = atomicAdd(&counters[0], 1ull);
+                item = __shfl_sync(0xffffffffu, item, 0);
+                if (item >= A.n_items) {
+                    exhausted = true;
+                    break;
+                }
+                const unsigned seg = (unsigned)(item % (unsigned long long)A.n_segments);
+                const unsigned long long blk = item / (unsigned long long)A.n_segments;
+                const unsigned blocks_per_tile = (unsigned)(A.blocks_per_tile_x * A.blocks_per_tile_y);
+                const unsigned local_tile = (unsigned)(blk / blocks_per_tile), in_tile = (unsigned)(blk % blocks_per_tile);
+                const unsigned tile = A.tile_offset + local_tile * A.tile_stride;
+                blk_x0 = (int)(tile % A.tiles_x) * A.tile_size + (int)(in_tile % A.blocks_per_tile_x) * 8;
+                blk_y0 = (int)(tile / A.tiles_x) * A.tile_size + (int)(in_tile / A.blocks_per_tile_x) * 4;
+                seg_s0 = (int)seg * A.seg_len;
+                pool_size = 32u * (unsigned)min(A.seg_len, A.n_local_samples - seg_s0);
+                pool_pos = 0;
+            }
+            const unsigned e = pool_pos + __popc(needy & lt_mask);
+            if (state == LANE_IDLE && e < pool_size) {
+                const int px = blk_x0 + (int)(e & 7u), py = blk_y0 + (int)((e >> 3) & 3u);
+                if (px < A.width && py < A.height) {
+                    rng.pixel = (uint32_t)(py * A.width + px);
+                    rng.sample = (uint32_t)(A.spp_begin + A.sample_offset + (seg_s0 + (int)(e >> 5)) * A.sample_stride);
+                    ray = camera_ray(S, px, py, rng);
+                    L = v3(0, 0, 0);
+                    T = v3(1, 1, 1);
+                    bounce = 0;
+                    origin_prim = PRIM_NONE;
+                    tr.init(S, kInf);
+                    state = tr.done() ? LANE_SHADE : LANE_TRAVERSE;
+                    if (STATS) { st.samples++; st.rays++; }
+                }
+            }
+            pool_pos += min((unsigned)__popc(needy), pool_size - pool_pos);
+            needy = __ballot_sync(0xffffffffu, state == LANE_IDLE);
+        }
+        if (__ballot_sync(0xffffffffu, state != LANE_IDLE) == 0u) break;  // pool dry, nothing in flight
+
+        // ---- 2. traversal phase ------------------------------------------------------------------
+        {
+            RayConst rc;
+            rc.set(ray);
+            while (true) {
+                // descend: every traversing lane that holds an interior node takes one step per
+                // iteration; lanes that reached a leaf wait, but only until the descending ones
+                // are a minority (1/kDescendDiv of the traversing lanes) -- those simply keep
+                // descending in the next round while the others intersect their leaves
+                while (true) {
+                    const bool descending = state == LANE_TRAVERSE && tr.cur >= 0;
+                    const unsigned dmask = __ballot_sync(0xffffffffu, descending);
+                    if (dmask == 0u) break;
+                    if (kDescendDiv > 0 && kDescendDiv * __popc(dmask) <= __popc(__ballot_sync(0xffffffffu, state == LANE_TRAVERSE))) break;
+                    if (descending) tr.interior<STATS>(S, rc, 0.001f, stack, &st, &overflow);
+                }
+                if (state == LANE_TRAVERSE && tr.cur < 0) {
+                    if (!tr.done()) tr.leaf<STATS>(S, ray, rc, 0.001f, origin_prim, stack, &st);
+                    if (tr.done()) state = LANE_SHADE;
+                }
+                const unsigned active = __ballot_sync(0xffffffffu, state == LANE_TRAVERSE);
+                if (active == 0u || __popc(active) < kTravThreshold) break;
+            }
+        }
+
+        // ---- 3. shade phase: Camera.txt:203-238 for the lanes whose traversal finished ------------
+        if (state == LANE_SHADE) {
+            Hit hit = tr.hit;
+            int medium = -1;
+            if (S.n_media > 0) medium = media_hit<STATS>(S, ray, 0.001f, hit.t, rng, bounce, &st);
+            bool done = false;
+            if (medium < 0 && hit.prim == PRIM_NONE) {
+                L = L + T * v3(S.background);
+                done = true;
+            } else {
+                Surface sf;
+                if (medium >= 0) {  // constant_medium.h:45-50
+                    const DevMedium& md = S.media[medium];
+                    sf.t = hit.t;
+                    sf.p = fma3(hit.t, ray.d, ray.o);
+                    sf.normal = v3(md.normal);
+                    sf.front = true;
+                    sf.u = sf.v = 0.0f;
+                    sf.material = md.material;
+                    sf.prim_id = -1;
+                    origin_prim = PRIM_NONE;
+                } else {
+                    complete_hit(S, ray, hit, sf, false);
+                    origin_prim = hit.prim;
+                }
+                const DevMaterial& m = S.mats[sf.material];
+                L = L + T * mat_emitted(S, m, sf);
+                float4 u4 = make_float4(0, 0, 0, 0);
+                if (m.type != RT_MAT_DIFFUSE_LIGHT && m.type != RT_MAT_EMISSIVE_LIGHT) u4 = rng.draw(bounce, RS_SCATTER);
+                V3 att;
+                Ray next;
+                if (!mat_scatter(S, m, ray, sf, u4, att, next)) {
+                    done = true;
+                } else {
+                    if (S.n_lights > 0) L = L + T * att * point_lighting(S, sf.p, sf.normal);
+                    T = T * att;
+                    ray = next;
+                    bounce++;
+                    if (bounce >= (uint32_t)A.max_depth) done = true;  // ray_color(depth <= 0) returns 0
+                }
+            }
+            if (done) {
+                unsigned long long* a = accum + 4ull * rng.pixel;
+                if (isfinite(L.x) && isfinite(L.y) && isfinite(L.z)) {
+                    atomicAdd(a + 0, __float2ull_rn(fminf(fmaxf(L.x, 0.0f), kSampleClamp) * kAccumScale));
+                    atomicAdd(a + 1, __float2ull_rn(fminf(fmaxf(L.y, 0.0f), kSampleClamp) * kAccumScale));
+                    atomicAdd(a + 2, __float2ull_rn(fminf(fmaxf(L.z, 0.0f), kSampleClamp) * kAccumScale));
+                } else {
+                    atomicAdd(a + 3, 1ull);
+                    if (STATS) st.nonfinite++;
+                }
+                state = LANE_IDLE;
+            } else {
+                tr.init(S, kInf);
+                state = tr.done() ? LANE_SHADE : LANE_TRAVERSE;
+                if (STATS) st.rays++;
+            }
+        }
+    }
+    if (overflow) atomicAdd(&counters[1], 1ull);
+    if (STATS) {
+        unsigned long long* g = reinterpret_cast<unsigned long long*>(gstats);
+        const unsigned long long* l = reinterpret_cast<const unsigned long long*>(&st);
+        for (unsigned i = 0; i < sizeof(Stats) / 8; i++) {
+            unsigned long long v = l[i];
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (lane == 0 && v) atomicAdd(g + i, v);
+        }
+    }
+}
+
 __global__ void aov_kernel(const __grid_constant__ DevScene S, int width, int height, int* __restrict__ prim_id,
                            float* __restrict__ t_out, float* __restrict__ normal, float* __restrict__ point,
                            float* __restrict__ uv, unsigned long long* counters) {
@@ -326,6 +533,7 @@ struct rt_ctx {
     rt_stats stats{};
     int cam_w = 0, cam_h = 0;  // frame the device camera block was computed for
     int sm_count = 0;
+    int kernel_version = 2;  // RT_B200_KERNEL=v1 selects the first (fixed-ownership) megakernel for A/B runs
     int blocks_per_sm[2] = {0, 0};
     bool pending_async = false;
 };
@@ -391,10 +599,19 @@ extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
     // local-memory traversal stacks live in L1: prefer L1 over shared memory
     cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], render_kernel<false>, 256, 0));
-    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], render_kernel<true>, 256, 0));
+    cudaFuncSetAttribute(render_kernel_v2<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel_v2<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    if (const char* kv = getenv("RT_B200_KERNEL")) ctx->kernel_version = (strcmp(kv, "v1") == 0) ? 1 : 2;
     cudaFuncAttributes fa;
-    CU(ctx, cudaFuncGetAttributes(&fa, render_kernel<false>));
+    if (ctx->kernel_version == 1) {
+        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], render_kernel<false>, 256, 0));
+        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], render_kernel<true>, 256, 0));
+        CU(ctx, cudaFuncGetAttributes(&fa, render_kernel<false>));
+    } else {
+        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], render_kernel_v2<false>, 256, 0));
+        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], render_kernel_v2<true>, 256, 0));
+        CU(ctx, cudaFuncGetAttributes(&fa, render_kernel_v2<false>));
+    }
     ctx->stats.regs_per_thread = fa.numRegs;
     ctx->stats.local_bytes_per_thread = (uint32_t)fa.localSizeBytes;
     ctx->stats.threads_per_block = 256;
@@ -748,6 +965,9 @@ extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
         d.material = m.material;
         D3 n = xf_dir(m.xform >= 0 ? &sc->xforms[m.xform] : nullptr, D3{1, 0, 0});
         d.normal[0] = (float)n.x; d.normal[1] = (float)n.y; d.normal[2] = (float)n.z;
+        d.sphere = -1;
+        if (m.boundary_count == 1 && (boundary_packed[m.boundary_first] >> 28) == PT_SPHERE)
+            d.sphere = (int)(boundary_packed[m.boundary_first] & 0x0fffffffu);
     }
     std::vector<DevLight> lights((size_t)sc->n_lights);
     for (int i = 0; i < sc->n_lights; i++) {
@@ -776,6 +996,7 @@ extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
 #undef UP
     S.root = bvh.root;
     S.n_nodes = (int)bvh.nodes.size();
+    S.n_world = sc->n_world;
     S.n_media = sc->n_media;
     S.n_lights = sc->n_lights;
     ctx->camera = sc->camera;
@@ -925,8 +1146,13 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
     if (!async) CU(ctx, cudaEventRecord(ctx->ev0, stream));
     ctx->stats.kernel_launches = 0;
     if (A.n_items > 0) {
-        if (stats) render_kernel<true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
-        else render_kernel<false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+        if (ctx->kernel_version == 1) {
+            if (stats) render_kernel<true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            else render_kernel<false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+        } else {
+            if (stats) render_kernel_v2<true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            else render_kernel_v2<false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+        }
         CU(ctx, cudaGetLastError());
         ctx->stats.kernel_launches = 1;
     }

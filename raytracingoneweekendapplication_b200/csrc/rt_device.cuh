@@ -24,7 +24,7 @@ namespace rtdev {
 
 enum : uint32_t { PT_SPHERE = 0, PT_MSPHERE = 1, PT_QUAD = 2, PT_TRI = 3 };
 constexpr uint32_t PRIM_NONE = 0xffffffffu;
-constexpr int STACK_SIZE = 48;
+constexpr int STACK_SIZE = 64;  // power of two (the index is masked); BVH2 depth of a SAH tree over 2^25 prims stays below
 
 struct DevMaterial {  // 32 B
     int type;
@@ -51,7 +51,7 @@ struct DevMedium {  // 48 B
     float neg_inv_density;  // -1 / (multiplicity * density)
     int material;
     float normal[3];  // R * (1,0,0)
-    int pad;
+    int sphere;  // >= 0: the boundary is this one static sphere (index into sph); -1: generic
     float bmin[3];
     float bmax_pad;
 };
@@ -66,6 +66,7 @@ struct DevScene {
     const float4* nodes;
     int root;
     int n_nodes;
+    int n_world;  // 0: every ray misses (the root link is not followed)
     const float4* sph;
     const float4* msph;
     const float4* quad;
@@ -171,6 +172,27 @@ struct Hit {
     float u, v;     // quad: alpha, beta; triangle: barycentric u, v
 };
 
+// sphere.h:33-46 verbatim in double.  Out of line: it is the rare path (a ray that starts within
+// r/16 of the surface of a sphere it did not start on) and keeping its DFMA/DSQRT/DDIV
+// sequences out of the traversal loop shrinks the loop's code and register footprint.
+__device__ __noinline__ bool sphere_roots_fp64(const double* cd, bool moving, const Ray& ray, float& t0, float& t1) {
+    double cx = cd[0], cy = cd[1], cz = cd[2], rr = cd[3];
+    if (moving) {
+        cx += (double)ray.time * cd[4]; cy += (double)ray.time * cd[5]; cz += (double)ray.time * cd[6];
+    }
+    double ox = cx - (double)ray.o.x, oy = cy - (double)ray.o.y, oz = cz - (double)ray.o.z;
+    double dx = ray.d.x, dy = ray.d.y, dz = ray.d.z;
+    double a = dx * dx + dy * dy + dz * dz;
+    double hh = dx * ox + dy * oy + dz * oz;
+    double cc = ox * ox + oy * oy + oz * oz - rr * rr;
+    double disc = hh * hh - a * cc;
+    if (disc < 0.0) return false;
+    double sq = sqrt(disc);
+    t0 = (float)((hh - sq) / a);
+    t1 = (float)((hh + sq) / a);
+    return true;
+}
+
 // sphere.h:32-49.  Robust FP32 form (distance from the centre to the ray line instead of
 // h*h - a*c), the exact c = 0 case for a ray that starts ON this sphere, and the
 // reference's own double-precision quadratic when the origin is within r/16 of the
@@ -190,20 +212,7 @@ __device__ __forceinline__ void hit_sphere(V3 c, float r, const double* cd, bool
         float cterm = dot(oc, oc) - r2;
         if (fabsf(cterm) < 0.125f * r2) {
             if (STATS) st->fp64_sphere++;
-            double cx = cd[0], cy = cd[1], cz = cd[2], rr = cd[3];
-            if (moving) {  // sphere.h:33 in double
-                cx += (double)ray.time * cd[4]; cy += (double)ray.time * cd[5]; cz += (double)ray.time * cd[6];
-            }
-            double ox = cx - (double)ray.o.x, oy = cy - (double)ray.o.y, oz = cz - (double)ray.o.z;
-            double dx = ray.d.x, dy = ray.d.y, dz = ray.d.z;
-            double a = dx * dx + dy * dy + dz * dz;
-            double hh = dx * ox + dy * oy + dz * oz;
-            double cc = ox * ox + oy * oy + oz * oz - rr * rr;
-            double disc = hh * hh - a * cc;
-            if (disc < 0.0) return;
-            double sq = sqrt(disc);
-            t0 = (float)((hh - sq) / a);
-            t1 = (float)((hh + sq) / a);
+            if (!sphere_roots_fp64(cd, moving, ray, t0, t1)) return;
         } else {
             V3 l = fma3(-k, ray.d, oc);
             float disc = r2 - dot(l, l);
@@ -289,114 +298,181 @@ __device__ __forceinline__ void hit_prim(const DevScene& S, uint32_t type, uint3
 
 // bvh.h:64-72 + aabb.h:61-85 + hittable_list.h:22-35, as an iterative stack traversal of the
 // flattened SAH tree: closest hit over (tmin, tmax).
-template <bool STATS>
-__device__ __forceinline__ void traverse(const DevScene& S, const Ray& ray, float tmin, float tmax, uint32_t origin_prim,
-                                         Hit& hit, Stats* st, int* overflow) {
-    hit.t = tmax;
-    hit.prim = PRIM_NONE;
-    hit.u = hit.v = 0.0f;
-    auto safe_inv = [](float d) { return 1.0f / (fabsf(d) > 1e-30f ? d : copysignf(1e-30f, d)); };
-    const float idx = safe_inv(ray.d.x), idy = safe_inv(ray.d.y), idz = safe_inv(ray.d.z);
-    const float ox = ray.o.x * idx, oy = ray.o.y * idy, oz = ray.o.z * idz;
-    const float inv_a = 1.0f / dot(ray.d, ray.d);
-    if (STATS) st->rays++;
+//
+// The traversal is a resumable state machine (Trav) so that the megakernel can suspend a
+// lane's ray between steps: `interior()` consumes one 64-byte node (two child boxes), `leaf()`
+// intersects the primitives of one leaf, both end by choosing the next link or popping the
+// stack; `done()` turns true when the stack runs dry.
+struct RayConst {  // per-ray constants of the slab test, recomputed when a traversal phase starts
+    float idx, idy, idz, ox, oy, oz, inv_a;
+    __device__ __forceinline__ void set(const Ray& ray) {
+        auto safe_inv = [](float d) { return 1.0f / (fabsf(d) > 1e-30f ? d : copysignf(1e-30f, d)); };
+        idx = safe_inv(ray.d.x); idy = safe_inv(ray.d.y); idz = safe_inv(ray.d.z);
+        ox = ray.o.x * idx; oy = ray.o.y * idy; oz = ray.o.z * idz;
+        inv_a = 1.0f / dot(ray.d, ray.d);
+    }
+};
 
-    int stack_link[STACK_SIZE];
-    float stack_t[STACK_SIZE];
-    int sp = 0;
-    int cur = S.root;
-    while (true) {
-        if (cur >= 0) {
-            const float4* n = S.nodes + 4 * (size_t)cur;
-            float4 a = ldg4(n), b = ldg4(n + 1), c = ldg4(n + 2), e = ldg4(n + 3);
-            if (STATS) { st->node_visits++; st->box_tests += 2; }
-            float lx0 = fmaf(a.x, idx, -ox), lx1 = fmaf(b.x, idx, -ox);
-            float ly0 = fmaf(a.y, idy, -oy), ly1 = fmaf(b.y, idy, -oy);
-            float lz0 = fmaf(a.z, idz, -oz), lz1 = fmaf(b.z, idz, -oz);
-            float ln = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), tmin));
-            float lf = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), hit.t));
-            float rx0 = fmaf(c.x, idx, -ox), rx1 = fmaf(e.x, idx, -ox);
-            float ry0 = fmaf(c.y, idy, -oy), ry1 = fmaf(e.y, idy, -oy);
-            float rz0 = fmaf(c.z, idz, -oz), rz1 = fmaf(e.z, idz, -oz);
-            float rn = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), tmin));
-            float rf = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), hit.t));
-            bool hl = ln <= lf, hr = rn <= rf;
-            int linkl = __float_as_int(a.w), linkr = __float_as_int(b.w);
-            if (hl && hr) {
-                bool swap = rn < ln;
-                int near_l = swap ? linkr : linkl, far_l = swap ? linkl : linkr;
-                float far_t = swap ? ln : rn;
-                if (sp < STACK_SIZE) {
-                    stack_link[sp] = far_l;
-                    stack_t[sp] = far_t;
-                    sp++;
-                } else {
-                    *overflow = 1;
-                }
-                cur = near_l;
-                continue;
-            } else if (hl) {
-                cur = linkl;
-                continue;
-            } else if (hr) {
-                cur = linkr;
-                continue;
-            }
-        } else {
-            uint32_t v = ~(uint32_t)cur;
-            uint32_t type = v >> 28, cnt = ((v >> 25) & 7u) + 1u, first = v & 0x1ffffffu;
-            for (uint32_t i = 0; i < cnt; i++) hit_prim<STATS>(S, type, first + i, ray, inv_a, tmin, origin_prim, hit, st);
-        }
-        // pop, skipping subtrees that start beyond the closest hit so far
-        bool found = false;
+constexpr int LINK_DONE = (int)0x80000000;  // negative, and not a leaf encoding (those are > -2^30)
+
+// Traversal state.  The stack is a separate local array of packed (entry distance, link)
+// pairs: keeping the scalars out of the indexed array lets the compiler hold them in
+// registers, and one 64-bit local store/load moves an entry.
+typedef unsigned long long StackEntry;
+__device__ __forceinline__ StackEntry pack_entry(int link, float t) {
+    return ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)link;
+}
+
+struct Trav {
+    Hit hit;
+    int cur;  // >= 0 interior node, < 0 leaf, LINK_DONE finished (also < 0)
+    int sp;
+
+    __device__ __forceinline__ void init(const DevScene& S, float tmax) {
+        hit.t = tmax;
+        hit.prim = PRIM_NONE;
+        hit.u = hit.v = 0.0f;
+        sp = 0;
+        cur = S.n_world > 0 ? S.root : LINK_DONE;
+    }
+    __device__ __forceinline__ bool done() const { return cur == LINK_DONE; }
+
+    // pop, skipping subtrees that start beyond the closest hit so far
+    __device__ __forceinline__ void pop(const StackEntry* stack) {
+        cur = LINK_DONE;
         while (sp > 0) {
             sp--;
-            if (stack_t[sp] <= hit.t) {
-                cur = stack_link[sp];
-                found = true;
+            const StackEntry e = stack[sp];
+            if (__uint_as_float((unsigned)(e >> 32)) <= hit.t) {
+                cur = (int)(unsigned)e;
                 break;
             }
         }
-        if (!found) break;
     }
+
+    // One 64-byte node = two child boxes (aabb.h:61-85 twice).  The choice of the next link is
+    // select-based: the four outcomes (both / left / right / none) share one instruction stream,
+    // the push is a predicated store, and only the (rare) "none" case branches into pop().
+    template <bool STATS>
+    __device__ __forceinline__ void interior(const DevScene& S, const RayConst& rc, float tmin, StackEntry* stack, Stats* st,
+                                             int* overflow) {
+        const float4* n = S.nodes + 4 * (size_t)cur;
+        float4 a = ldg4(n), b = ldg4(n + 1), c = ldg4(n + 2), e = ldg4(n + 3);
+        if (STATS) { st->node_visits++; st->box_tests += 2; }
+        float lx0 = fmaf(a.x, rc.idx, -rc.ox), lx1 = fmaf(b.x, rc.idx, -rc.ox);
+        float ly0 = fmaf(a.y, rc.idy, -rc.oy), ly1 = fmaf(b.y, rc.idy, -rc.oy);
+        float lz0 = fmaf(a.z, rc.idz, -rc.oz), lz1 = fmaf(b.z, rc.idz, -rc.oz);
+        float ln = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), tmin));
+        float lf = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), hit.t));
+        float rx0 = fmaf(c.x, rc.idx, -rc.ox), rx1 = fmaf(e.x, rc.idx, -rc.ox);
+        float ry0 = fmaf(c.y, rc.idy, -rc.oy), ry1 = fmaf(e.y, rc.idy, -rc.oy);
+        float rz0 = fmaf(c.z, rc.idz, -rc.oz), rz1 = fmaf(e.z, rc.idz, -rc.oz);
+        float rn = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), tmin));
+        float rf = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), hit.t));
+        const bool hl = ln <= lf, hr = rn <= rf;
+        const int linkl = __float_as_int(a.w), linkr = __float_as_int(b.w);
+        const bool right_first = hr && (!hl || rn < ln);
+        const int near_l = right_first ? linkr : linkl;
+        const int far_l = right_first ? linkl : linkr;
+        const float far_t = right_first ? ln : rn;
+        if (hl && hr) {
+            stack[sp & (STACK_SIZE - 1)] = pack_entry(far_l, far_t);
+            if (sp >= STACK_SIZE) *overflow = 1;
+            sp++;
+        }
+        if (hl || hr) cur = near_l;
+        else pop(stack);
+    }
+
+    template <bool STATS>
+    __device__ __forceinline__ void leaf(const DevScene& S, const Ray& ray, const RayConst& rc, float tmin, uint32_t origin_prim,
+                                         const StackEntry* stack, Stats* st) {
+        uint32_t v = ~(uint32_t)cur;
+        uint32_t type = v >> 28, cnt = ((v >> 25) & 7u) + 1u, first = v & 0x1ffffffu;
+        for (uint32_t i = 0; i < cnt; i++) hit_prim<STATS>(S, type, first + i, ray, rc.inv_a, tmin, origin_prim, hit, st);
+        pop(stack);
+    }
+};
+
+template <bool STATS>
+__device__ __forceinline__ void traverse(const DevScene& S, const Ray& ray, float tmin, float tmax, uint32_t origin_prim,
+                                         Hit& hit, Stats* st, int* overflow) {
+    RayConst rc;
+    rc.set(ray);
+    if (STATS) st->rays++;
+    Trav tr;
+    StackEntry stack[STACK_SIZE];
+    tr.init(S, tmax);
+    while (!tr.done()) {
+        if (tr.cur >= 0) tr.interior<STATS>(S, rc, tmin, stack, st, overflow);
+        else tr.leaf<STATS>(S, ray, rc, tmin, origin_prim, stack, st);
+    }
+    hit = tr.hit;
 }
 
-// Closest hit of `ray` over (lo, hi) against a medium's boundary primitives (no BVH:
-// a boundary is one sphere or the six quads of a box in every scene of the reference).
-template <bool STATS>
-__device__ __forceinline__ float boundary_hit(const DevScene& S, const DevMedium& m, const Ray& ray, float inv_a, float lo,
-                                              float hi, Stats* st) {
+// The two boundary->hit calls of constant_medium.h:23-27 against an arbitrary boundary (no
+// BVH: a boundary is one sphere or the six quads of a box in every scene of the reference).
+// Out of line: only media whose boundary is not a single static sphere come here.
+__device__ __noinline__ bool boundary_pair_generic(const DevScene& S, int bfirst, int bcount, const Ray& ray, float inv_a, float& t1,
+                                                   float& t2) {
+    const float inf = __int_as_float(0x7f800000);
     Hit h;
-    h.t = hi;
-    h.prim = PRIM_NONE;
-    h.u = h.v = 0.0f;
-    for (int i = 0; i < m.bcount; i++) {
-        uint32_t ref = __ldg(S.boundary + m.bfirst + i);
-        if (STATS) st->boundary_tests++;
-        hit_prim<false>(S, ref >> 28, ref & 0x0fffffffu, ray, inv_a, lo, PRIM_NONE, h, st);
+    h.t = inf; h.prim = PRIM_NONE; h.u = h.v = 0.0f;
+    for (int i = 0; i < bcount; i++) {
+        uint32_t ref = __ldg(S.boundary + bfirst + i);
+        hit_prim<false>(S, ref >> 28, ref & 0x0fffffffu, ray, inv_a, -inf, PRIM_NONE, h, nullptr);  // interval::universe
     }
-    return h.prim == PRIM_NONE ? __int_as_float(0x7fc00000) : h.t;  // NaN = miss
+    if (h.prim == PRIM_NONE) return false;
+    t1 = h.t;
+    h.t = inf; h.prim = PRIM_NONE;
+    for (int i = 0; i < bcount; i++) {
+        uint32_t ref = __ldg(S.boundary + bfirst + i);
+        hit_prim<false>(S, ref >> 28, ref & 0x0fffffffu, ray, inv_a, t1 + 0.0001f, PRIM_NONE, h, nullptr);
+    }
+    if (h.prim == PRIM_NONE) return false;
+    t2 = h.t;
+    return true;
 }
 
 // constant_medium.h:20-53 for every medium, against the closest surface hit so far.
 // Returns the index of the medium that scattered the ray (or -1) and updates t_hit.
+// A boundary that is one static sphere (both media of the book-2 scene) takes ONE quadratic:
+// sphere::hit over the universe returns the smaller root, and over (t1 + 1e-4, inf) the larger
+// one if it lies beyond t1 + 1e-4 (sphere.h:44-49).
 template <bool STATS>
 __device__ __forceinline__ int media_hit(const DevScene& S, const Ray& ray, float tmin, float& t_hit, const Rng& rng,
                                          uint32_t bounce, Stats* st) {
     int which = -1;
-    const float inv_a = 1.0f / dot(ray.d, ray.d);
-    const float ray_length = sqrtf(dot(ray.d, ray.d));
+    const float a = dot(ray.d, ray.d);
+    const float inv_a = 1.0f / a;
+    const float ray_length = sqrtf(a);
     float4 u4 = make_float4(0, 0, 0, 0);
     for (int m = 0; m < S.n_media; m++) {
         if ((m & 3) == 0) u4 = rng.draw(bounce, RS_MEDIUM + (m >> 2));
         float u = (m & 3) == 0 ? u4.x : ((m & 3) == 1 ? u4.y : ((m & 3) == 2 ? u4.z : u4.w));
         const DevMedium& md = S.media[m];
-        if (STATS) st->medium_queries++;
-        const float inf = __int_as_float(0x7f800000);
-        float t1 = boundary_hit<STATS>(S, md, ray, inv_a, -inf, inf, st);  // interval::universe
-        if (!(t1 == t1)) continue;
-        float t2 = boundary_hit<STATS>(S, md, ray, inv_a, t1 + 0.0001f, inf, st);
-        if (!(t2 == t2)) continue;
+        if (STATS) { st->medium_queries++; st->boundary_tests += 2 * md.bcount; }
+        float t1, t2;
+        if (md.sphere >= 0) {
+            float4 s = ldg4(S.sph + md.sphere);
+            V3 oc = v3(s) - ray.o;
+            float k = dot(ray.d, oc) * inv_a;
+            float r2 = s.w * s.w;
+            float cterm = dot(oc, oc) - r2;
+            if (fabsf(cterm) < 0.125f * r2) {
+                if (!sphere_roots_fp64(S.sph_d + 4 * (size_t)md.sphere, false, ray, t1, t2)) continue;
+            } else {
+                V3 l = fma3(-k, ray.d, oc);
+                float disc = r2 - dot(l, l);
+                if (disc < 0.0f) continue;
+                float sq = sqrtf(disc * inv_a);
+                t1 = k - sq;
+                t2 = k + sq;
+            }
+            if (!(t2 > t1 + 0.0001f)) continue;
+        } else {
+            if (!boundary_pair_generic(S, md.bfirst, md.bcount, ray, inv_a, t1, t2)) continue;
+        }
         if (t1 < tmin) t1 = tmin;
         if (t2 > t_hit) t2 = t_hit;
         if (t1 >= t2) continue;
@@ -448,7 +524,7 @@ __device__ __forceinline__ float perlin_turb(const DevScene& S, int pidx, V3 p, 
     return fabsf(accum);
 }
 
-__device__ __forceinline__ V3 tex_value(const DevScene& S, int tex, float u, float v, V3 p) {
+__device__ __noinline__ V3 tex_value_general(const DevScene& S, int tex, float u, float v, V3 p) {
     // checker textures select a child and recurse (texture.h:42-50, 66-76): iterate instead
     for (int level = 0; level < 16; level++) {
         const DevTexture& t = S.texs[tex];
@@ -481,6 +557,13 @@ __device__ __forceinline__ V3 tex_value(const DevScene& S, int tex, float u, flo
     return v3(0, 0, 0);
 }
 
+// solid_color is by far the most common texture: keep it inline, send the rest out of line
+__device__ __forceinline__ V3 tex_value(const DevScene& S, int tex, float u, float v, V3 p) {
+    const DevTexture& t = S.texs[tex];
+    if (t.type == RT_TEX_SOLID) return v3(t.color);
+    return tex_value_general(S, tex, u, v, p);
+}
+
 // ---------------------------------------------------------------------------------
 // hit record completion + materials (material.h)
 // ---------------------------------------------------------------------------------
@@ -499,6 +582,26 @@ __device__ __forceinline__ void sphere_uv(V3 n, float& u, float& v) {  // sphere
     float phi = atan2f(-n.z, n.x) + pi;
     u = phi / (2.0f * pi);
     v = theta / pi;
+}
+
+// The accepted sphere hit re-solved in double (sphere.h:33-52 verbatim); out of line, once per
+// sphere hit.
+__device__ __noinline__ void refine_sphere_hit(double cx, double cy, double cz, double rr, const Ray& ray, float t_approx, float& t_out,
+                                               V3& p_out, V3& outward) {
+    double ox = cx - (double)ray.o.x, oy = cy - (double)ray.o.y, oz = cz - (double)ray.o.z;
+    double dx = ray.d.x, dy = ray.d.y, dz = ray.d.z;
+    double a = dx * dx + dy * dy + dz * dz;
+    double hh = dx * ox + dy * oy + dz * oz;
+    double cc = ox * ox + oy * oy + oz * oz - rr * rr;
+    double sq = sqrt(fmax(hh * hh - a * cc, 0.0));
+    double inv_a = 1.0 / a;
+    double ta = (hh - sq) * inv_a, tb = (hh + sq) * inv_a;
+    double td = fabs(ta - (double)t_approx) <= fabs(tb - (double)t_approx) ? ta : tb;
+    double px = (double)ray.o.x + td * dx, py = (double)ray.o.y + td * dy, pz = (double)ray.o.z + td * dz;
+    double inv_r = 1.0 / rr;
+    t_out = (float)td;
+    p_out = v3((float)px, (float)py, (float)pz);
+    outward = v3((float)((px - cx) * inv_r), (float)((py - cy) * inv_r), (float)((pz - cz) * inv_r));  // sphere.h:52
 }
 
 __device__ __forceinline__ void complete_hit(const DevScene& S, const Ray& ray, const Hit& hit, Surface& sf, bool want_uv) {
@@ -524,20 +627,18 @@ __device__ __forceinline__ void complete_hit(const DevScene& S, const Ray& ray, 
             rr = cd[3];
             sh = __ldg(S.msph_sh + idx);
         }
+        // FP32 suffices unless the sphere is small relative to its distance (the FP32 hit point is
+        // only good to ulp(|p|), which the normal magnifies by 1/r) or the ray starts near the
+        // surface of a big sphere (cancellation in |oc|^2 - r^2)
         {
-            double ox = cx - (double)ray.o.x, oy = cy - (double)ray.o.y, oz = cz - (double)ray.o.z;
-            double dx = ray.d.x, dy = ray.d.y, dz = ray.d.z;
-            double a = dx * dx + dy * dy + dz * dz;
-            double hh = dx * ox + dy * oy + dz * oz;
-            double cc = ox * ox + oy * oy + oz * oz - rr * rr;
-            double sq = sqrt(fmax(hh * hh - a * cc, 0.0));
-            double ta = (hh - sq) / a, tb = (hh + sq) / a;
-            double td = fabs(ta - (double)hit.t) <= fabs(tb - (double)hit.t) ? ta : tb;
-            double px = (double)ray.o.x + td * dx, py = (double)ray.o.y + td * dy, pz = (double)ray.o.z + td * dz;
-            double inv_r = 1.0 / rr;
-            sf.t = (float)td;
-            sf.p = v3((float)px, (float)py, (float)pz);
-            outward = v3((float)((px - cx) * inv_r), (float)((py - cy) * inv_r), (float)((pz - cz) * inv_r));  // sphere.h:52
+            const float fcx = (float)cx, fcy = (float)cy, fcz = (float)cz, fr = (float)rr;
+            V3 oc = v3(fcx, fcy, fcz) - ray.o;
+            float oc2 = dot(oc, oc), r2 = fr * fr;
+            if (want_uv || oc2 > 64.0f * r2 || fabsf(oc2 - r2) < 0.125f * r2) {
+                refine_sphere_hit(cx, cy, cz, rr, ray, hit.t, sf.t, sf.p, outward);
+            } else {
+                outward = (1.0f / fr) * (sf.p - v3(fcx, fcy, fcz));  // sphere.h:52
+            }
         }
         sf.material = sh.x;
         sf.prim_id = sh.z;

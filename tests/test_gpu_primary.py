@@ -19,7 +19,7 @@ def check(r):
     # identity: >= 99.99 % of the pixels the reference itself decides robustly (see
     # helpers.undecidable_pixels; they must stay a sliver of the frame)
     assert r["id_match"] >= 0.9999, r
-    assert r["undecidable"] <= 0.003 * r["pixels"], r
+    assert r["undecidable"] <= 0.01 * r["pixels"], r
     assert r["t_within_1e5"] >= 0.9999 and r["t_rel_max"] <= 10 * T_TOL, r
     # normals: the accepted sphere hit is re-solved in FP64, so what remains is the FP32
     # REPRESENTATION of the ray itself (1e-7 relative in the direction), which a sphere of
