@@ -311,17 +311,21 @@ def run_b200(args):
         n_e2e = max(2, min(args.steps, 4))
         barrier()
         t0 = time.perf_counter()
+        t_up = t_rd = t_dl = 0.0
         for i in range(n_e2e):
+            ta = time.perf_counter()
             ctx.upload(sc)                                                   # H2D: the flattened scene (+ host BVH build)
+            tb = time.perf_counter()
             ctx.render(width, height, spp_step, max_depth=depth, seed=1, spp_begin=i * spp_step, **shard)
             if world > 1:
                 ptr, nb = ctx.accum_buffer()
-                # wrap the library-owned buffer for the NCCL reduce
-                buf = _as_tensor(ptr, nb)
-                sharding.reduce_frame(buf)
+                sharding.reduce_frame(_as_tensor(ptr, nb))                   # the library-owned buffer, over NCCL
                 torch.cuda.synchronize()
+            tc = time.perf_counter()
             if rank == 0:
                 ctx.lib.rt_download(ctx._h, spp_step, None, frame8.ctypes.data)   # D2H: the RGB8 frame
+            td = time.perf_counter()
+            t_up += tb - ta; t_rd += tc - tb; t_dl += td - tc
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -329,7 +333,8 @@ def run_b200(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": width * height * spp_step * n_e2e / float(tt[0]) * 1e-6, "unit": "Msamples/s",
                "h2d_bytes_per_step": scene_bytes(sc.desc), "d2h_bytes_per_step": width * height * 3, "steps": n_e2e,
-               "call": "rt_upload_scene + rt_render + rt_download(rgb8) per step (what camera::render does), host buffers"}
+               "call": "rt_upload_scene + rt_render + rt_download(rgb8) per step (what camera::render does), host buffers",
+               "ms_upload": 1e3 * t_up / n_e2e, "ms_render": 1e3 * t_rd / n_e2e, "ms_download": 1e3 * t_dl / n_e2e}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
