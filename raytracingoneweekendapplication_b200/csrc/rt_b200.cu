@@ -519,7 +519,16 @@ struct rt_ctx {
     std::string error;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::vector<void*> scene_allocs;
+    // the whole device scene lives in ONE arena, staged in pinned host memory and moved with
+    // one copy per rt_upload_scene; both grow on demand and are reused across uploads
+    unsigned char* arena = nullptr;
+    size_t arena_cap = 0;
+    unsigned char* staging = nullptr;
+    size_t staging_cap = 0;
+    // persistent output buffers of rt_download
+    float* out_lin = nullptr;
+    unsigned char* out_rgb8 = nullptr;
+    size_t out_pixels = 0;
     DevScene scene{};
     bool has_scene = false;
     rt_camera camera{};
@@ -554,23 +563,27 @@ static int fail(rt_ctx* ctx, int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));      \
     } while (0)
 
-static void free_scene(rt_ctx* ctx) {
-    for (void* p : ctx->scene_allocs) cudaFree(p);
-    ctx->scene_allocs.clear();
-    ctx->has_scene = false;
+static void free_scene(rt_ctx* ctx) { ctx->has_scene = false; }
+
+static void release_buffers(rt_ctx* ctx) {
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->staging) cudaFreeHost(ctx->staging);
+    if (ctx->out_lin) cudaFree(ctx->out_lin);
+    if (ctx->out_rgb8) cudaFree(ctx->out_rgb8);
+    ctx->arena = ctx->staging = ctx->out_rgb8 = nullptr;
+    ctx->out_lin = nullptr;
+    ctx->arena_cap = ctx->staging_cap = ctx->out_pixels = 0;
 }
 
-template <class T>
-static int upload(rt_ctx* ctx, const std::vector<T>& v, const T** out) {
-    *out = nullptr;
-    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
-    void* p = nullptr;
-    CU(ctx, cudaMalloc(&p, bytes));
-    ctx->scene_allocs.push_back(p);
-    if (!v.empty()) CU(ctx, cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    *out = (const T*)p;
-    return RT_OK;
-}
+// layout of the scene arena: every block 256-byte aligned
+struct ArenaPlan {
+    size_t size = 0;
+    size_t add(size_t bytes) {
+        size_t off = (size + 255) & ~(size_t)255;
+        size = off + std::max<size_t>(bytes, 16);
+        return off;
+    }
+};
 
 extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
     if (!out) return RT_ERR_INVALID;
@@ -623,6 +636,7 @@ extern "C" void rt_destroy(rt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
+    release_buffers(ctx);
     if (ctx->accum && !ctx->accum_external) cudaFree(ctx->accum);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->dstats) cudaFree(ctx->dstats);
@@ -934,14 +948,9 @@ extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
     }
     std::vector<DevImage> images((size_t)sc->n_images);
     for (int i = 0; i < sc->n_images; i++) {
-        const rt_image& im = sc->images[i];
-        std::vector<unsigned char> bytes(im.rgb, im.rgb + (size_t)im.width * im.height * 3);
-        const unsigned char* dptr = nullptr;
-        rc = upload(ctx, bytes, &dptr);
-        if (rc != RT_OK) return rc;
-        images[i].rgb = dptr;
-        images[i].w = im.width;
-        images[i].h = im.height;
+        images[i].rgb = nullptr;  // patched once the arena address is known
+        images[i].w = sc->images[i].width;
+        images[i].h = sc->images[i].height;
     }
     std::vector<float4> perlin_vec((size_t)sc->n_perlins * 256);
     std::vector<unsigned char> perlin_perm((size_t)sc->n_perlins * 768);
@@ -986,14 +995,45 @@ extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
 
     DevScene& S = ctx->scene;
     std::memset(&S, 0, sizeof S);
-#define UP(vec, field)                          \
-    rc = upload(ctx, vec, &S.field);            \
-    if (rc != RT_OK) return rc;
+    // ---- one arena, one copy -----------------------------------------------------------------
+    ArenaPlan plan;
+    std::vector<size_t> img_off((size_t)sc->n_images);
+    for (int i = 0; i < sc->n_images; i++) img_off[i] = plan.add((size_t)sc->images[i].width * sc->images[i].height * 3);
+    struct Block { const void* src; size_t bytes, off; const void** field; };
+    std::vector<Block> blocks;
+#define UP(vec, field) blocks.push_back(Block{vec.data(), vec.size() * sizeof(vec[0]), plan.add(vec.size() * sizeof(vec[0])), (const void**)&S.field});
     UP(nodes, nodes) UP(sph, sph) UP(msph, msph) UP(quad, quad) UP(tri, tri) UP(sph_d, sph_d) UP(msph_d, msph_d) UP(quad_d, quad_d)
     UP(tri_d, tri_d) UP(sph_sh, sph_sh) UP(msph_sh, msph_sh) UP(quad_sh, quad_sh) UP(tri_sh, tri_sh) UP(xrot, xrot) UP(media, media)
     UP(boundary_packed, boundary) UP(mats, mats) UP(texs, texs) UP(images, images) UP(perlin_vec, perlin_vec)
     UP(perlin_perm, perlin_perm) UP(lights, lights)
 #undef UP
+    if (plan.size > ctx->arena_cap) {
+        if (ctx->arena) cudaFree(ctx->arena);
+        ctx->arena = nullptr;
+        ctx->arena_cap = 0;
+        size_t cap = plan.size + plan.size / 4;
+        if (cudaMalloc(&ctx->arena, cap) != cudaSuccess) return fail(ctx, RT_ERR_NOMEM, "rt_upload_scene: cannot allocate %zu bytes of device memory", cap);
+        ctx->arena_cap = cap;
+    }
+    if (plan.size > ctx->staging_cap) {
+        if (ctx->staging) cudaFreeHost(ctx->staging);
+        ctx->staging = nullptr;
+        ctx->staging_cap = 0;
+        size_t cap = plan.size + plan.size / 4;
+        if (cudaHostAlloc(&ctx->staging, cap, cudaHostAllocDefault) != cudaSuccess)
+            return fail(ctx, RT_ERR_NOMEM, "rt_upload_scene: cannot allocate %zu bytes of pinned host memory", cap);
+        ctx->staging_cap = cap;
+    }
+    for (int i = 0; i < sc->n_images; i++) {
+        images[i].rgb = ctx->arena + img_off[i];
+        std::memcpy(ctx->staging + img_off[i], sc->images[i].rgb, (size_t)sc->images[i].width * sc->images[i].height * 3);
+    }
+    for (const Block& b : blocks) {
+        if (b.bytes) std::memcpy(ctx->staging + b.off, b.src, b.bytes);
+        *b.field = ctx->arena + b.off;
+    }
+    CU(ctx, cudaMemcpyAsync(ctx->arena, ctx->staging, plan.size, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     S.root = bvh.root;
     S.n_nodes = (int)bvh.nodes.size();
     S.n_world = sc->n_world;
@@ -1205,18 +1245,24 @@ extern "C" int rt_download(rt_ctx* ctx, int32_t total_spp, float* rgb_linear, ui
     CU(ctx, cudaDeviceSynchronize());
     ctx->pending_async = false;
     const int n = ctx->acc_w * ctx->acc_h;
-    float* dlin = nullptr;
-    unsigned char* d8 = nullptr;
-    if (rgb_linear) CU(ctx, cudaMalloc(&dlin, (size_t)n * 3 * sizeof(float)));
-    if (rgb8) CU(ctx, cudaMalloc(&d8, (size_t)n * 3));
+    if ((size_t)n > ctx->out_pixels) {
+        if (ctx->out_lin) cudaFree(ctx->out_lin);
+        if (ctx->out_rgb8) cudaFree(ctx->out_rgb8);
+        ctx->out_lin = nullptr;
+        ctx->out_rgb8 = nullptr;
+        ctx->out_pixels = 0;
+        if (cudaMalloc(&ctx->out_lin, (size_t)n * 3 * sizeof(float)) != cudaSuccess || cudaMalloc(&ctx->out_rgb8, (size_t)n * 3) != cudaSuccess)
+            return fail(ctx, RT_ERR_NOMEM, "rt_download: cannot allocate the output buffers");
+        ctx->out_pixels = (size_t)n;
+    }
+    float* dlin = rgb_linear ? ctx->out_lin : nullptr;
+    unsigned char* d8 = rgb8 ? ctx->out_rgb8 : nullptr;
     double inv = 1.0 / ((double)kAccumScale * (double)total_spp);
     resolve_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->accum, n, inv, dlin, d8);
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && rgb_linear) e = cudaMemcpyAsync(rgb_linear, dlin, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && rgb8) e = cudaMemcpyAsync(rgb8, d8, (size_t)n * 3, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e == cudaSuccess && rgb_linear) e = cudaMemcpy(rgb_linear, dlin, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && rgb8) e = cudaMemcpy(rgb8, d8, (size_t)n * 3, cudaMemcpyDeviceToHost);
-    if (dlin) cudaFree(dlin);
-    if (d8) cudaFree(d8);
     if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "rt_download: %s", cudaGetErrorString(e));
     return RT_OK;
 }
