@@ -298,6 +298,14 @@ def run_b200(args):
     except OSError:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # DRAM traffic of one launch, from the committed ncu capture of this very command/config
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if tr.get("workload") == f"{args.scene} {width}x{height} {spp_step}spp" and world == 1:
+            traffic = tr["traffic_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
     ach_tflops = (flops / (launch_ms * 1e-3)) * 1e-12
     ach_gbs = (nbytes / (launch_ms * 1e-3)) * 1e-9
 
@@ -359,12 +367,12 @@ def run_b200(args):
             "mrays_per_s": float(counters[2]) / (launch_ms * 1e-3) * 1e-6,
             "rays_per_sample": float(counters[2]) / (width * height * spp_step),
             "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": ach_tflops / fp32_peak if fp32_peak else None, "traffic": None,
+                         "frac": ach_tflops / fp32_peak if fp32_peak else None, "traffic": traffic,
                          "peak_source": "measured here: FP32 FMA microbenchmark (rt_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
                          "algorithmic": "24/box + 30/sphere + 48/quad + 44/triangle + 40/boundary test + 50/ray shading (SURVEY 8d), "
                                         "counted on the device for this launch", "launch_ms": launch_ms, "per": "rank 0 launch"},
             "roofline_mem": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                             "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                             "traffic": traffic, "algorithmic_bytes": nbytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                              "algorithmic": "64 B/node visit + 16/48/48 B per sphere/quad/triangle test + 16 B/ray shading fetch + "
                                             "32 B/pixel accumulation", "note": "BVH and primitives are L1/L2 resident: this is a "
                                             "cache-bandwidth figure reported against the HBM roof"},

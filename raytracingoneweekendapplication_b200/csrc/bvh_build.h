@@ -55,11 +55,14 @@ struct Result {
 };
 
 constexpr int kBins = 16;
-constexpr int kMaxLeaf = 4;
+struct Tuning {
+    int max_leaf = 4;       // primitives per leaf (<= 8, the link encoding has 3 count bits)
+    float trav_cost = 1.0f; // cost of one node visit relative to a sphere test
+};
 
 class Builder {
   public:
-    Builder(std::vector<Prim>& prims, Result& out) : P(prims), R(out) {}
+    Builder(std::vector<Prim>& prims, Result& out, Tuning t = Tuning()) : P(prims), R(out), tune(t) {}
 
     void run() {
         ids.resize(P.size());
@@ -81,6 +84,7 @@ class Builder {
   private:
     std::vector<Prim>& P;
     Result& R;
+    Tuning tune;
     std::vector<uint32_t> ids;
     uint32_t type_cursor[4];
 
@@ -144,11 +148,11 @@ class Builder {
                 acc.grow(bin_box[i]);
                 c += bin_cost[i];
                 if (c == 0 || right_cost[i + 1] == 0) continue;
-                float cost = 1.0f + (acc.area() * c + right_area[i + 1] * right_cost[i + 1]) / parent_area;
+                float cost = tune.trav_cost + (acc.area() * c + right_area[i + 1] * right_cost[i + 1]) / parent_area;
                 if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = i; }
             }
         }
-        const bool can_leaf = n <= (uint32_t)kMaxLeaf && single_type(a, b);
+        const bool can_leaf = n <= (uint32_t)tune.max_leaf && single_type(a, b);
         if (can_leaf && (best_axis < 0 || total_cost <= best_cost)) return make_leaf(a, b);
 
         uint32_t mid;

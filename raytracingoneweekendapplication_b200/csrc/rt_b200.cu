@@ -872,7 +872,10 @@ extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
     }
     rtbvh::Result bvh;
     {
-        rtbvh::Builder builder(prims, bvh);
+        rtbvh::Tuning tune;  // RT_B200_MAX_LEAF / RT_B200_TRAV_COST: tuning experiments only
+        if (const char* e = getenv("RT_B200_MAX_LEAF")) tune.max_leaf = std::max(1, std::min(8, atoi(e)));
+        if (const char* e = getenv("RT_B200_TRAV_COST")) tune.trav_cost = (float)atof(e);
+        rtbvh::Builder builder(prims, bvh, tune);
         builder.run();
     }
 
