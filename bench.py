@@ -34,6 +34,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SCENE_DEFAULT = "final"
+WORKLOADS = {"final": "C5 RTOW book-2 final scene (BASELINE configs[4])", "book1": "C1 RTOW book-1 final scene (configs[0])",
+             "cornell": "C2 Cornell box (configs[1])", "cornell_smoke": "C3 Cornell box with smoke (configs[2])",
+             "mesh": "C4 triangle-mesh scene (configs[3])"}
 FLOPS = {"box": 24, "sphere": 30, "quad": 48, "tri": 44, "boundary": 40, "shade": 50}
 BYTES = {"node": 64, "sphere": 16, "quad": 48, "tri": 48, "boundary": 32, "shade": 16}
 
@@ -163,7 +166,7 @@ def run_reference(args):
         "impl": "reference", "metric": "path-tracing throughput", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(runs)), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C5 RTOW book-2 final scene {width}x{height}, depth {depth} (BASELINE configs[4])",
+        "config": {"workload": f"{WORKLOADS.get(args.scene, args.scene)} {width}x{height}, depth {depth}",
                    "scene": args.scene, "step": runs[0]["sample"] if runs else ""},
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": runs[0]["cores"] if runs else 0,
                          "kind": runs[0]["kind"] if runs else "reference", "sample": runs[0]["sample"] if runs else ""},
@@ -357,8 +360,8 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"C5 RTOW book-2 final scene {width}x{height}, depth {depth}, {spp_step * args.steps} spp "
-                            f"({spp_step} spp per step; BASELINE configs[4])",
+                "workload": f"{WORKLOADS.get(args.scene, args.scene)} {width}x{height}, depth {depth}, {spp_step * args.steps} spp "
+                            f"({spp_step} spp per step)",
                 "scene": args.scene, "width": width, "height": height, "spp_per_step": spp_step, "depth": depth,
                 "sharding": {1: "tiles 16x16 interleaved", 2: "samples interleaved"}[plan.mode] if world > 1 else "none",
                 "l2": "frame accumulation buffer %d MB > 126 MB L2 is re-read every step; the scene (~1 MB) is "
@@ -401,6 +404,11 @@ def _as_tensor(ptr: int, nbytes: int):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version
+    # there) are sent to stderr for the duration of the run, the line goes to the real stdout
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     args = parse()
     if args.impl == "reference":
         return run_reference(args)

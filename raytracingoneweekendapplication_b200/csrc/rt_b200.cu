@@ -1165,13 +1165,14 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
     const bool stats = (p->flags & RT_FLAG_STATS) != 0;
     const int bps = ctx->blocks_per_sm[stats ? 1 : 0];
     const int grid = ctx->sm_count * (bps > 0 ? bps : 1);
-    // segment length: enough work items to keep every resident warp busy ~8 times over,
+    // segment length: enough work items to keep every resident warp busy ~64 times over,
     // but never shorter than 1 sample (fixed-point sums make the split result-neutral)
     const unsigned long long pixel_blocks = (unsigned long long)A.n_local_tiles * A.blocks_per_tile_x * A.blocks_per_tile_y;
     const unsigned long long resident_warps = (unsigned long long)grid * 8ull;
     int n_seg = 1;
     if (A.n_local_samples > 0 && pixel_blocks > 0) {
-        unsigned long long want = (resident_warps * 8ull + pixel_blocks - 1) / pixel_blocks;
+        // >= 64 items per resident warp: the end-of-kernel tail is one item long
+        unsigned long long want = (resident_warps * 64ull + pixel_blocks - 1) / pixel_blocks;
         if (want < 1) want = 1;
         if (want > (unsigned long long)A.n_local_samples) want = A.n_local_samples;
         n_seg = (int)want;
