@@ -157,3 +157,24 @@ def test_full_4k_frame_properties(ctx, scene_of):
     img = whole.reshape(h, w, 4)
     assert (img[..., 3] == 0).all()
     assert img[:200, 1200:2200, :3].mean() > img[:200, :400, :3].mean()   # the ceiling light is up there
+
+
+def test_both_kernel_versions_render_the_same_bits(built, scene_of):
+    """render_kernel (v1, fixed ownership) and render_kernel_v2 (warp streams) schedule the same
+    samples completely differently; fixed-point sums make the frames bit-identical."""
+    import os
+
+    from raytracingoneweekendapplication_b200 import capi
+
+    frames = []
+    for version in ("v1", "v2"):
+        os.environ["RT_B200_KERNEL"] = version
+        try:
+            c = capi.Context(0)
+        finally:
+            os.environ.pop("RT_B200_KERNEL", None)
+        c.upload(scene_of("kitchen_sink"))
+        c.render(160, 90, 6, seed=8)
+        frames.append(c.download(6).copy())
+        c.close()
+    assert np.array_equal(frames[0], frames[1])
