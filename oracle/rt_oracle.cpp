@@ -615,6 +615,23 @@ bool init_scene(Scene& sc, const rt_scene_desc* d) {
 
 using namespace oracle;
 
+// rows [0, n) over all host threads (the checker itself has no shared mutable state)
+template <class F>
+static void parallel_rows(int n, F body) {
+    std::atomic<int> next{0};
+    int threads = std::max(1, (int)std::thread::hardware_concurrency());
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&]() {
+            for (;;) {
+                int j = next.fetch_add(1);
+                if (j >= n) break;
+                body(j);
+            }
+        });
+    for (auto& th : pool) th.join();
+}
+
 extern "C" {
 
 // Mean radiance (and single-sample variance) per pixel, samples [spp_begin, spp_begin+spp).
@@ -663,7 +680,7 @@ int oracle_primary(const rt_scene_desc* d, int width, int height, int32_t* ids, 
     Scene sc;
     if (!init_scene(sc, d)) return 1;
     init_camera(sc, width, height);
-    for (int j = 0; j < height; j++)
+    parallel_rows(height, [&](int j) {
         for (int i = 0; i < width; i++) {
             Ray r;
             r.o = sc.center;
@@ -681,6 +698,7 @@ int oracle_primary(const rt_scene_desc* d, int width, int height, int32_t* ids, 
             uv[2 * px] = hit ? rec.u : 0;
             uv[2 * px + 1] = hit ? rec.v : 0;
         }
+    });
     return 0;
 }
 
@@ -688,18 +706,21 @@ int oracle_primary(const rt_scene_desc* d, int width, int height, int32_t* ids, 
 int oracle_hit(const rt_scene_desc* d, int n, const double* rays, int32_t* ids, double* t, double* normal, double* uv) {
     Scene sc;
     if (!init_scene(sc, d)) return 1;
-    for (int i = 0; i < n; i++) {
-        const double* q = rays + 9 * (size_t)i;
-        Ray r;
-        r.o = mk(q); r.d = mk(q + 3); r.tm = q[6];
-        HitRec rec;
-        bool hit = surface_hit(sc, r, q[7], q[8], rec);
-        ids[i] = hit ? rec.prim : -1;
-        t[i] = hit ? rec.t : 0;
-        for (int k = 0; k < 3; k++) normal[3 * i + k] = hit ? rec.normal[k] : 0;
-        uv[2 * i] = hit ? rec.u : 0;
-        uv[2 * i + 1] = hit ? rec.v : 0;
-    }
+    const int chunk = 4096;
+    parallel_rows((n + chunk - 1) / chunk, [&](int c) {
+        for (int i = c * chunk; i < std::min(n, (c + 1) * chunk); i++) {
+            const double* q = rays + 9 * (size_t)i;
+            Ray r;
+            r.o = mk(q); r.d = mk(q + 3); r.tm = q[6];
+            HitRec rec;
+            bool hit = surface_hit(sc, r, q[7], q[8], rec);
+            ids[i] = hit ? rec.prim : -1;
+            t[i] = hit ? rec.t : 0;
+            for (int k = 0; k < 3; k++) normal[3 * i + k] = hit ? rec.normal[k] : 0;
+            uv[2 * i] = hit ? rec.u : 0;
+            uv[2 * i + 1] = hit ? rec.v : 0;
+        }
+    });
     return 0;
 }
 

@@ -40,9 +40,9 @@ def test_primary_hits_match_reference_fixture(ctx, scene_of, name):
 
 
 @pytest.mark.parametrize("name,w,h", [("book1", 400, 225), ("cornell", 600, 600), ("cornell_smoke", 600, 600),
-                                      ("mesh", 960, 540), ("final", 960, 540)])
+                                      ("mesh", 1920, 1080), ("final", 3840, 2160)])
 def test_primary_hits_match_oracle_at_baseline_frames(ctx, scene_of, name, w, h):
-    """The BASELINE frame (C4/C5 at half resolution per axis) against the CPU restatement,
+    """The full BASELINE frame of every config (C5: 8.3 M primary rays) against the CPU restatement,
     which is itself pinned bit-exactly to the reference fixtures (test_oracle_port.py)."""
     from oracle import port
 
