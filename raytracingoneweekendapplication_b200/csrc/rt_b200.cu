@@ -24,6 +24,7 @@
 #include "bvh_build.h"
 #include "rt_b200.h"
 #include "rt_device.cuh"
+#include "rt_wavefront.cuh"
 
 using namespace rtdev;
 
@@ -542,7 +543,10 @@ struct rt_ctx {
     rt_stats stats{};
     int cam_w = 0, cam_h = 0;  // frame the device camera block was computed for
     int sm_count = 0;
-    int kernel_version = 2;  // RT_B200_KERNEL=v1 selects the first (fixed-ownership) megakernel for A/B runs
+    int kernel_version = 2;  // RT_B200_KERNEL=v1 | v2 | wf: which formulation of the bounce loop runs (A/B measurements)
+    rtwf::Pool pool{};       // wavefront path pool (allocated on first use)
+    void* pool_mem = nullptr;
+    int wf_blocks_per_sm[2] = {0, 0};
     int blocks_per_sm[2] = {0, 0};
     bool pending_async = false;
 };
@@ -567,6 +571,9 @@ static void free_scene(rt_ctx* ctx) { ctx->has_scene = false; }
 
 static void release_buffers(rt_ctx* ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->pool_mem) cudaFree(ctx->pool_mem);
+    ctx->pool_mem = nullptr;
+    ctx->pool = rtwf::Pool{};
     if (ctx->staging) cudaFreeHost(ctx->staging);
     if (ctx->out_lin) cudaFree(ctx->out_lin);
     if (ctx->out_rgb8) cudaFree(ctx->out_rgb8);
@@ -614,7 +621,13 @@ extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
     cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    if (const char* kv = getenv("RT_B200_KERNEL")) ctx->kernel_version = (strcmp(kv, "v1") == 0) ? 1 : 2;
+    if (const char* kv = getenv("RT_B200_KERNEL")) ctx->kernel_version = strcmp(kv, "v1") == 0 ? 1 : (strcmp(kv, "wf") == 0 ? 3 : 2);
+    cudaFuncSetAttribute(rtwf::wf_extend<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(rtwf::wf_extend<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(rtwf::wf_shade<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(rtwf::wf_shade<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->wf_blocks_per_sm[0], rtwf::wf_extend<false>, 256, 0));
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->wf_blocks_per_sm[1], rtwf::wf_shade<false>, 256, 0));
     cudaFuncAttributes fa;
     if (ctx->kernel_version == 1) {
         CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], render_kernel<false>, 256, 0));
@@ -875,8 +888,7 @@ extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
         rtbvh::Tuning tune;  // RT_B200_MAX_LEAF / RT_B200_TRAV_COST: tuning experiments only
         if (const char* e = getenv("RT_B200_MAX_LEAF")) tune.max_leaf = std::max(1, std::min(8, atoi(e)));
         if (const char* e = getenv("RT_B200_TRAV_COST")) tune.trav_cost = (float)atof(e);
-        rtbvh::Builder builder(prims, bvh, tune);
-        builder.run();
+        rtbvh::build_bvh(prims, bvh, tune);
     }
 
     // ---- device arrays in leaf order, boundaries appended ------------------------------
@@ -1113,6 +1125,71 @@ extern "C" int rt_sync(rt_ctx* ctx) {
     return RT_OK;
 }
 
+// ---------------------------------------------------------------------------------
+// wavefront driver (RT_B200_KERNEL=wf): generate once, then (swap, extend, shade) per bounce
+// of the pool until the sample stream is exhausted and no path is alive
+// ---------------------------------------------------------------------------------
+static int launch_wavefront(rt_ctx* ctx, const RenderArgs& A, cudaStream_t stream, bool stats, unsigned long long pixel_blocks) {
+    rtwf::Stream W;
+    std::memset(&W, 0, sizeof W);
+    W.width = A.width; W.height = A.height; W.max_depth = A.max_depth; W.spp_begin = A.spp_begin;
+    W.n_local_samples = A.n_local_samples; W.sample_stride = A.sample_stride; W.sample_offset = A.sample_offset;
+    W.tiles_x = A.tiles_x; W.tile_size = A.tile_size; W.tile_stride = A.tile_stride; W.tile_offset = A.tile_offset;
+    W.blocks_per_tile_x = A.blocks_per_tile_x; W.blocks_per_tile_y = A.blocks_per_tile_y;
+    W.total = pixel_blocks * 32ull * (unsigned long long)A.n_local_samples;
+    W.k0 = A.k0; W.k1 = A.k1;
+
+    const uint32_t want_cap = 1u << 20;  // 1 Mi paths in flight: 3.4 waves of 148 x 2048 threads
+    if (!ctx->pool_mem) {
+        const size_t per_path = 5 * sizeof(float4) + sizeof(uint2) + 2 * sizeof(uint32_t);
+        const size_t bytes = (size_t)want_cap * per_path + 256;
+        if (cudaMalloc(&ctx->pool_mem, bytes) != cudaSuccess) return fail(ctx, RT_ERR_NOMEM, "rt_render: cannot allocate the wavefront path pool (%zu bytes)", bytes);
+        unsigned char* p = (unsigned char*)ctx->pool_mem;
+        rtwf::Pool& P = ctx->pool;
+        P.ctr = (unsigned long long*)p; p += 256;
+        P.ray_o = (float4*)p; p += (size_t)want_cap * sizeof(float4);
+        P.ray_d = (float4*)p; p += (size_t)want_cap * sizeof(float4);
+        P.thr = (float4*)p; p += (size_t)want_cap * sizeof(float4);
+        P.rad = (float4*)p; p += (size_t)want_cap * sizeof(float4);
+        P.hit = (float4*)p; p += (size_t)want_cap * sizeof(float4);
+        P.id = (uint2*)p; p += (size_t)want_cap * sizeof(uint2);
+        P.list[0] = (uint32_t*)p; p += (size_t)want_cap * sizeof(uint32_t);
+        P.list[1] = (uint32_t*)p;
+        P.capacity = want_cap;
+    }
+    rtwf::Pool P = ctx->pool;
+    unsigned long long live = std::min<unsigned long long>(W.total, want_cap);
+    P.capacity = (uint32_t)((live + 255) / 256 * 256);
+    if (P.capacity > want_cap) P.capacity = want_cap;
+    if (P.capacity == 0) return RT_OK;
+    CU(ctx, cudaMemsetAsync(P.ctr, 0, 64, stream));
+    rtwf::wf_generate<<<P.capacity / 256, 256, 0, stream>>>(ctx->scene, W, P);
+    uint32_t launches = 1;
+    const int grid_e = ctx->sm_count * std::max(1, ctx->wf_blocks_per_sm[0]);
+    const int grid_s = ctx->sm_count * std::max(1, ctx->wf_blocks_per_sm[1]);
+    unsigned long long h[8];
+    for (int batch = 0; batch < (1 << 20); batch++) {
+        for (int it = 0; it < 16; it++) {
+            rtwf::wf_swap<<<1, 1, 0, stream>>>(P);
+            if (stats) {
+                rtwf::wf_extend<true><<<grid_e, 256, 0, stream>>>(ctx->scene, P, ctx->dstats);
+                rtwf::wf_shade<true><<<grid_s, 256, 0, stream>>>(ctx->scene, W, P, ctx->accum, ctx->dstats);
+            } else {
+                rtwf::wf_extend<false><<<grid_e, 256, 0, stream>>>(ctx->scene, P, ctx->dstats);
+                rtwf::wf_shade<false><<<grid_s, 256, 0, stream>>>(ctx->scene, W, P, ctx->accum, ctx->dstats);
+            }
+            launches += 3;
+        }
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaMemcpyAsync(h, P.ctr, sizeof h, cudaMemcpyDeviceToHost, stream));
+        CU(ctx, cudaStreamSynchronize(stream));
+        if (h[3] == 0) break;  // nothing appended by the last shade: every path ended and the stream is dry
+    }
+    CU(ctx, cudaMemcpyAsync(ctx->counters + 1, P.ctr + 1, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
+    ctx->stats.kernel_launches = launches;
+    return RT_OK;
+}
+
 extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
     if (!ctx) return RT_ERR_INVALID;
     if (!p || p->struct_size != sizeof(rt_render_params)) return fail(ctx, RT_ERR_INVALID, "rt_render: bad params struct");
@@ -1190,7 +1267,10 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
     if (!async) CU(ctx, cudaEventRecord(ctx->ev0, stream));
     ctx->stats.kernel_launches = 0;
     if (A.n_items > 0) {
-        if (ctx->kernel_version == 1) {
+        if (ctx->kernel_version == 3) {
+            rc = launch_wavefront(ctx, A, stream, stats, pixel_blocks);
+            if (rc != RT_OK) return rc;
+        } else if (ctx->kernel_version == 1) {
             if (stats) render_kernel<true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
             else render_kernel<false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
         } else {
@@ -1198,7 +1278,7 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
             else render_kernel_v2<false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
         }
         CU(ctx, cudaGetLastError());
-        ctx->stats.kernel_launches = 1;
+        if (ctx->kernel_version != 3) ctx->stats.kernel_launches = 1;
     }
     ctx->stats.blocks = grid;
     ctx->stats.samples = (uint64_t)A.n_local_samples * ((mode == RT_SHARD_TILES && count > 1) ? 0 : (uint64_t)p->width * p->height);

@@ -160,14 +160,15 @@ def test_full_4k_frame_properties(ctx, scene_of):
 
 
 def test_both_kernel_versions_render_the_same_bits(built, scene_of):
-    """render_kernel (v1, fixed ownership) and render_kernel_v2 (warp streams) schedule the same
-    samples completely differently; fixed-point sums make the frames bit-identical."""
+    """render_kernel (v1, fixed ownership), render_kernel_v2 (warp streams) and the wavefront
+    pipeline (rt_wavefront.cuh) schedule the same samples completely differently; fixed-point
+    sums make the frames bit-identical."""
     import os
 
     from raytracingoneweekendapplication_b200 import capi
 
     frames = []
-    for version in ("v1", "v2"):
+    for version in ("v1", "v2", "wf"):
         os.environ["RT_B200_KERNEL"] = version
         try:
             c = capi.Context(0)
@@ -178,3 +179,4 @@ def test_both_kernel_versions_render_the_same_bits(built, scene_of):
         frames.append(c.download(6).copy())
         c.close()
     assert np.array_equal(frames[0], frames[1])
+    assert np.array_equal(frames[0], frames[2])   # the wavefront pipeline too
