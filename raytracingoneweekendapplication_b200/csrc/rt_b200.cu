@@ -134,12 +134,13 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Dev
                     origin_prim = hit.prim;
                 }
                 const DevMaterial& m = S.mats[sf.material];
-                L = L + T * mat_emitted(S, m, sf);
                 float4 u4 = make_float4(0, 0, 0, 0);
                 if (m.type != RT_MAT_DIFFUSE_LIGHT && m.type != RT_MAT_EMISSIVE_LIGHT) u4 = rng.draw(bounce, RS_SCATTER);
-                V3 att;
+                V3 att, emitted;
                 Ray next;
-                if (!mat_scatter(S, m, ray, sf, u4, att, next)) {
+                const bool scattered = shade_surface(S, m, ray, sf, u4, emitted, att, next);
+                L = L + T * emitted;
+                if (!scattered) {
                     done = true;
                 } else {
                     if (S.n_lights > 0) L = L + T * att * point_lighting(S, sf.p, sf.normal);
@@ -346,12 +347,13 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __g
                     origin_prim = hit.prim;
                 }
                 const DevMaterial& m = S.mats[sf.material];
-                L = L + T * mat_emitted(S, m, sf);
                 float4 u4 = make_float4(0, 0, 0, 0);
                 if (m.type != RT_MAT_DIFFUSE_LIGHT && m.type != RT_MAT_EMISSIVE_LIGHT) u4 = rng.draw(bounce, RS_SCATTER);
-                V3 att;
+                V3 att, emitted;
                 Ray next;
-                if (!mat_scatter(S, m, ray, sf, u4, att, next)) {
+                const bool scattered = shade_surface(S, m, ray, sf, u4, emitted, att, next);
+                L = L + T * emitted;
+                if (!scattered) {
                     done = true;
                 } else {
                     if (S.n_lights > 0) L = L + T * att * point_lighting(S, sf.p, sf.normal);

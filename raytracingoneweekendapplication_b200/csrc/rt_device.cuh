@@ -136,7 +136,10 @@ __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 // ---------------------------------------------------------------------------------
 constexpr uint32_t RS_CAMERA = 0, RS_DEFOCUS = 1, RS_SCATTER = 16, RS_MEDIUM = 32;
 
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#ifndef RT_PHILOX_ATTR
+#define RT_PHILOX_ATTR __forceinline__  // out of line costs 10 % on C5 (call ABI spills); measured
+#endif
+__device__ RT_PHILOX_ATTR uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -682,77 +685,93 @@ __device__ __forceinline__ V3 random_unit_vector(float ux, float uy, float uz) {
 __device__ __forceinline__ V3 reflect(V3 v, V3 n) { return v - 2.0f * dot(v, n) * n; }
 __device__ __forceinline__ bool near_zero(V3 v) { return fabsf(v.x) < 1e-8f && fabsf(v.y) < 1e-8f && fabsf(v.z) < 1e-8f; }
 
-// material::emitted (material.h:14,99-101,111-113)
+// The author's `specular` material (material.h:145-167).  Out of line: powf alone is ~150
+// instructions and the material appears in one scene.
+__device__ __noinline__ V3 specular_direction(V3 unit, V3 refl, V3 ruv, V3 normal, float shininess) {
+    V3 diffuse = ruv;  // random_on_hemisphere (vec3.h:116-124)
+    if (!(dot(diffuse, normal) > 0.0f)) diffuse = -diffuse;
+    float factor = powf(1.0f - dot(refl, unit), shininess);
+    V3 dir = factor * refl + (1.0f - factor) * diffuse;
+    if (near_zero(dir)) dir = normal;
+    return dir;
+}
+
+// material::emitted (material.h:14,99-101,111-113) and material::scatter (material.h:29-38,
+// 47-74, 82-88, 129-134, 145-167) of one hit.  `u4` holds the uniforms of this bounce (see Rng).
+// Returns false when the path ends here (absorbed, or a light).  Written so that the five
+// materials share what they have in common -- the texture lookup, the unit vector of
+// vec3.h:107-115, the normalised incoming direction and its mirror image -- and differ in a
+// handful of instructions each: the material switch is the most divergent code of the shade
+// phase, and its size is instruction-cache footprint.
+__device__ __forceinline__ bool shade_surface(const DevScene& S, const DevMaterial& m, const Ray& in, const Surface& sf, float4 u4,
+                                              V3& emitted, V3& attenuation, Ray& out) {
+    out.o = sf.p;
+    out.time = in.time;
+    out.d = sf.normal;
+    V3 texc = v3(0, 0, 0);
+    if (m.tex >= 0) texc = tex_value(S, m.tex, sf.u, sf.v, sf.p);
+    emitted = v3(0, 0, 0);
+    attenuation = texc;
+    if (m.type == RT_MAT_DIFFUSE_LIGHT || m.type == RT_MAT_EMISSIVE_LIGHT) {  // material.h:17-19, 99-101, 116-118
+        emitted = texc;
+        return false;
+    }
+    const V3 ruv = random_unit_vector(u4.x, u4.y, u4.z);
+    if (m.type == RT_MAT_LAMBERTIAN) {  // the common case first, with nothing it does not need
+        V3 dir = sf.normal + ruv;
+        if (near_zero(dir)) dir = sf.normal;
+        out.d = dir;
+        return true;
+    }
+    if (m.type == RT_MAT_ISOTROPIC) {
+        out.d = ruv;
+        return true;
+    }
+    const V3 unit = normalize(in.d);
+    const float cos_in = dot(unit, sf.normal);
+    const V3 refl = unit - (2.0f * cos_in) * sf.normal;  // reflect(unit, n), vec3.h:125-127
+    attenuation = v3(m.albedo);
+    if (m.type == RT_MAT_METAL) {
+        // unit_vector(reflect(d, n)) == reflect(unit_vector(d), n) (material.h:83-84)
+        V3 dir = fma3(m.param, ruv, normalize(refl));
+        out.d = dir;
+        return dot(dir, sf.normal) > 0.0f;
+    }
+    if (m.type == RT_MAT_DIELECTRIC) {
+        attenuation = v3(1.0f, 1.0f, 1.0f);
+        const float ri = sf.front ? __fdividef(1.0f, m.param) : m.param;
+        const float cos_theta = fminf(-cos_in, 1.0f);
+        const float sin_theta = sqrtf(fmaxf(1.0f - cos_theta * cos_theta, 0.0f));
+        float r0 = __fdividef(1.0f - ri, 1.0f + ri);
+        r0 = r0 * r0;
+        const float x = 1.0f - cos_theta;
+        const float reflectance = r0 + (1.0f - r0) * (x * x) * (x * x) * x;
+        if (ri * sin_theta > 1.0f || reflectance > u4.w) {
+            out.d = refl;
+        } else {  // vec3.h:128-133
+            V3 perp = ri * (unit + cos_theta * sf.normal);
+            V3 para = -sqrtf(fabsf(1.0f - dot(perp, perp))) * sf.normal;
+            out.d = perp + para;
+        }
+        return true;
+    }
+    out.d = specular_direction(unit, refl, ruv, sf.normal, m.param);  // RT_MAT_SPECULAR
+    return true;
+}
+
+// kept for the probes and the first kernel version: the same thing in two calls
 __device__ __forceinline__ V3 mat_emitted(const DevScene& S, const DevMaterial& m, const Surface& sf) {
     if (m.type == RT_MAT_DIFFUSE_LIGHT || m.type == RT_MAT_EMISSIVE_LIGHT) return tex_value(S, m.tex, sf.u, sf.v, sf.p);
     return v3(0, 0, 0);
 }
-
-// material::scatter (material.h:29-38, 47-74, 82-88, 129-134, 145-167).  `u4` holds the
-// uniforms of this bounce (see Rng).  Returns false when the ray is absorbed.
 __device__ __forceinline__ bool mat_scatter(const DevScene& S, const DevMaterial& m, const Ray& in, const Surface& sf, float4 u4,
                                             V3& attenuation, Ray& out) {
-    out.o = sf.p;
-    out.time = in.time;
-    switch (m.type) {
-        case RT_MAT_LAMBERTIAN: {
-            V3 dir = sf.normal + random_unit_vector(u4.x, u4.y, u4.z);
-            if (near_zero(dir)) dir = sf.normal;
-            out.d = dir;
-            attenuation = tex_value(S, m.tex, sf.u, sf.v, sf.p);
-            return true;
-        }
-        case RT_MAT_METAL: {
-            V3 refl = reflect(in.d, sf.normal);
-            refl = normalize(refl) + m.param * random_unit_vector(u4.x, u4.y, u4.z);
-            out.d = refl;
-            attenuation = v3(m.albedo);
-            return dot(refl, sf.normal) > 0.0f;
-        }
-        case RT_MAT_DIELECTRIC: {
-            attenuation = v3(1.0f, 1.0f, 1.0f);
-            float ri = sf.front ? (1.0f / m.param) : m.param;
-            V3 unit = normalize(in.d);
-            float cos_theta = fminf(dot(-unit, sf.normal), 1.0f);
-            float sin_theta = sqrtf(fmaxf(1.0f - cos_theta * cos_theta, 0.0f));
-            bool cannot_refract = ri * sin_theta > 1.0f;
-            float r0 = (1.0f - ri) / (1.0f + ri);
-            r0 = r0 * r0;
-            float x = 1.0f - cos_theta;
-            float reflectance = r0 + (1.0f - r0) * (x * x) * (x * x) * x;
-            if (cannot_refract || reflectance > u4.w) {
-                out.d = reflect(unit, sf.normal);
-            } else {  // vec3.h:128-133
-                V3 perp = ri * (unit + cos_theta * sf.normal);
-                V3 para = -sqrtf(fabsf(1.0f - dot(perp, perp))) * sf.normal;
-                out.d = perp + para;
-            }
-            return true;
-        }
-        case RT_MAT_ISOTROPIC: {
-            out.d = random_unit_vector(u4.x, u4.y, u4.z);
-            attenuation = tex_value(S, m.tex, sf.u, sf.v, sf.p);
-            return true;
-        }
-        case RT_MAT_SPECULAR: {
-            V3 unit = normalize(in.d);
-            V3 refl = reflect(unit, sf.normal);
-            V3 diffuse = random_unit_vector(u4.x, u4.y, u4.z);  // random_on_hemisphere (vec3.h:116-124)
-            if (!(dot(diffuse, sf.normal) > 0.0f)) diffuse = -diffuse;
-            float factor = powf(1.0f - dot(refl, unit), m.param);
-            V3 dir = factor * refl + (1.0f - factor) * diffuse;
-            if (near_zero(dir)) dir = sf.normal;
-            out.d = dir;
-            attenuation = v3(m.albedo);
-            return true;
-        }
-        default:
-            return false;  // diffuse_light / emissive_light: material.h:17-19, 116-118
-    }
+    V3 emitted;
+    return shade_surface(S, m, in, sf, u4, emitted, attenuation, out);
 }
 
 // Camera.txt:240-272: unshadowed point lights
-__device__ __forceinline__ V3 point_lighting(const DevScene& S, V3 p, V3 normal) {
+__device__ __noinline__ V3 point_lighting(const DevScene& S, V3 p, V3 normal) {
     V3 result = v3(0, 0, 0);
     for (int i = 0; i < S.n_lights; i++) {
         const DevLight& l = S.lights[i];

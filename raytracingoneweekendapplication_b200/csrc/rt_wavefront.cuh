@@ -251,12 +251,13 @@ __global__ void __launch_bounds__(256, 3) wf_shade(const __grid_constant__ DevSc
                     origin_prim = hit.prim;
                 }
                 const DevMaterial& m = S.mats[sf.material];
-                L = L + T * mat_emitted(S, m, sf);
                 float4 u4 = make_float4(0, 0, 0, 0);
                 if (m.type != RT_MAT_DIFFUSE_LIGHT && m.type != RT_MAT_EMISSIVE_LIGHT) u4 = rng.draw(bounce, RS_SCATTER);
-                V3 att;
+                V3 att, emitted;
                 Ray next;
-                if (!mat_scatter(S, m, ray, sf, u4, att, next)) {
+                const bool scattered = shade_surface(S, m, ray, sf, u4, emitted, att, next);
+                L = L + T * emitted;
+                if (!scattered) {
                     done = true;
                 } else {
                     if (S.n_lights > 0) L = L + T * att * point_lighting(S, sf.p, sf.normal);
