@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Dev
 #define RT_MIN_BLOCKS 3
 #endif
 #ifndef RT_DESCEND_DIV
-#define RT_DESCEND_DIV 4
+#define RT_DESCEND_DIV 0
 #endif
 constexpr int kTravThreshold = RT_TRAV_THRESHOLD;
 constexpr int kDescendDiv = RT_DESCEND_DIV;

@@ -316,7 +316,8 @@ struct RayConst {  // per-ray constants of the slab test, recomputed when a trav
     }
 };
 
-constexpr int LINK_DONE = (int)0x80000000;  // negative, and not a leaf encoding (those are > -2^30)
+constexpr int LINK_DONE = (int)0x80000000;
+  // negative, and not a leaf encoding (those are > -2^30)
 
 // Traversal state.  The stack is a separate local array of packed (entry distance, link)
 // pairs: keeping the scalars out of the indexed array lets the compiler hold them in
