@@ -218,7 +218,7 @@ constexpr int kTravThreshold = RT_TRAV_THRESHOLD;
 constexpr int kDescendDiv = RT_DESCEND_DIV;
 enum : int { LANE_IDLE = 0, LANE_TRAVERSE = 1, LANE_SHADE = 2 };
 
-template <bool STATS>
+template <bool STATS, bool LITE>
 __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A,
                                                         unsigned long long* __restrict__ accum,
                                                         unsigned long long* __restrict__ counters, Stats* __restrict__ gstats) {
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __g
                 if (px < A.width && py < A.height) {
                     rng.pixel = (uint32_t)(py * A.width + px);
                     rng.sample = (uint32_t)(A.spp_begin + A.sample_offset + (seg_s0 + (int)(e >> 5)) * A.sample_stride);
-                    ray = camera_ray(S, px, py, rng);
+                    ray = camera_ray<LITE>(S, px, py, rng);
                     L = v3(0, 0, 0);
                     T = v3(1, 1, 1);
                     bounce = 0;
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __g
                     if (descending) tr.interior<STATS>(S, rc, 0.001f, stack, &st, &overflow);
                 }
                 if (state == LANE_TRAVERSE && tr.cur < 0) {
-                    if (!tr.done()) tr.leaf<STATS>(S, ray, rc, 0.001f, origin_prim, stack, &st);
+                    if (!tr.done()) tr.leaf<STATS, LITE>(S, ray, rc, 0.001f, origin_prim, stack, &st);
                     if (tr.done()) state = LANE_SHADE;
                 }
                 const unsigned active = __ballot_sync(0xffffffffu, state == LANE_TRAVERSE);
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __g
                 if (!scattered) {
                     done = true;
                 } else {
-                    if (S.n_lights > 0) L = L + T * att * point_lighting(S, sf.p, sf.normal);
+                    if (!LITE && S.n_lights > 0) L = L + T * att * point_lighting(S, sf.p, sf.normal);
                     T = T * att;
                     ray = next;
                     bounce++;
@@ -534,6 +534,7 @@ struct rt_ctx {
     size_t out_pixels = 0;
     DevScene scene{};
     bool has_scene = false;
+    bool scene_lite = false;  // no triangles, no point lights, no defocus: the LITE kernel instance applies
     rt_camera camera{};
     // accumulation
     unsigned long long* accum = nullptr;
@@ -621,8 +622,9 @@ extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
     // local-memory traversal stacks live in L1: prefer L1 over shared memory
     cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(render_kernel_v2<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(render_kernel_v2<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel_v2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel_v2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel_v2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     if (const char* kv = getenv("RT_B200_KERNEL")) ctx->kernel_version = strcmp(kv, "v1") == 0 ? 1 : (strcmp(kv, "wf") == 0 ? 3 : 2);
     cudaFuncSetAttribute(rtwf::wf_extend<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(rtwf::wf_extend<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -636,9 +638,9 @@ extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
         CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], render_kernel<true>, 256, 0));
         CU(ctx, cudaFuncGetAttributes(&fa, render_kernel<false>));
     } else {
-        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], render_kernel_v2<false>, 256, 0));
-        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], render_kernel_v2<true>, 256, 0));
-        CU(ctx, cudaFuncGetAttributes(&fa, render_kernel_v2<false>));
+        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], render_kernel_v2<false, false>, 256, 0));
+        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], render_kernel_v2<true, false>, 256, 0));
+        CU(ctx, cudaFuncGetAttributes(&fa, render_kernel_v2<false, false>));
     }
     ctx->stats.regs_per_thread = fa.numRegs;
     ctx->stats.local_bytes_per_thread = (uint32_t)fa.localSizeBytes;
@@ -1057,6 +1059,7 @@ extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
     S.n_media = sc->n_media;
     S.n_lights = sc->n_lights;
     ctx->camera = sc->camera;
+    ctx->scene_lite = tri.empty() && sc->n_lights == 0 && !(sc->camera.defocus_angle > 0);
     ctx->cam_w = ctx->cam_h = 0;
     ctx->has_scene = true;
     ctx->stats.bvh_nodes = (uint32_t)bvh.nodes.size();
@@ -1276,8 +1279,11 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
             if (stats) render_kernel<true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
             else render_kernel<false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
         } else {
-            if (stats) render_kernel_v2<true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
-            else render_kernel_v2<false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            // LITE: no triangles, no point lights, no defocus blur in this scene (see hit_prim)
+            const bool lite = ctx->scene_lite && !getenv("RT_B200_NO_LITE");
+            if (stats) render_kernel_v2<true, false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            else if (lite) render_kernel_v2<false, true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            else render_kernel_v2<false, false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
         }
         CU(ctx, cudaGetLastError());
         if (ctx->kernel_version != 3) ctx->stats.kernel_launches = 1;

@@ -17,6 +17,7 @@
 // there is no index indirection.  Media boundaries live at the tail of the same arrays.
 #pragma once
 #include <cuda_runtime.h>
+
 #include <stdint.h>
 #include "rt_b200.h"
 
@@ -272,7 +273,10 @@ __device__ __forceinline__ void hit_tri(float4 t0, float4 t1, float4 t2, const R
     hit.v = v;
 }
 
-template <bool STATS>
+// LITE: the scene has no triangles (and, elsewhere, no point lights and no defocus): the
+// production kernel is also compiled without those features, because in one megakernel every
+// feature costs every scene registers and instruction-cache (C5 +4 % without them).
+template <bool STATS, bool LITE = false>
 __device__ __forceinline__ void hit_prim(const DevScene& S, uint32_t type, uint32_t idx, const Ray& ray, float inv_a, float tmin,
                                          uint32_t origin_prim, Hit& hit, Stats* st) {
     uint32_t prim = (type << 28) | idx;
@@ -285,7 +289,7 @@ __device__ __forceinline__ void hit_prim(const DevScene& S, uint32_t type, uint3
         if (prim == origin_prim) return;  // a ray leaving a planar primitive cannot hit it again
         const float4* q = S.quad + 3 * (size_t)idx;
         hit_quad(ldg4(q), ldg4(q + 1), ldg4(q + 2), ray, tmin, prim, hit);
-    } else if (type == PT_TRI) {
+    } else if (!LITE && type == PT_TRI) {
         if (STATS) st->tri_tests++;
         if (prim == origin_prim) return;
         const float4* t = S.tri + 3 * (size_t)idx;
@@ -388,12 +392,12 @@ struct Trav {
         else pop(stack);
     }
 
-    template <bool STATS>
+    template <bool STATS, bool LITE = false>
     __device__ __forceinline__ void leaf(const DevScene& S, const Ray& ray, const RayConst& rc, float tmin, uint32_t origin_prim,
                                          const StackEntry* stack, Stats* st) {
         uint32_t v = ~(uint32_t)cur;
         uint32_t type = v >> 28, cnt = ((v >> 25) & 7u) + 1u, first = v & 0x1ffffffu;
-        for (uint32_t i = 0; i < cnt; i++) hit_prim<STATS>(S, type, first + i, ray, rc.inv_a, tmin, origin_prim, hit, st);
+        for (uint32_t i = 0; i < cnt; i++) hit_prim<STATS, LITE>(S, type, first + i, ray, rc.inv_a, tmin, origin_prim, hit, st);
         pop(stack);
     }
 };
@@ -793,6 +797,7 @@ __device__ __noinline__ V3 point_lighting(const DevScene& S, V3 p, V3 normal) {
 // Camera.txt:177-200 get_ray.  Directions are built relative to the camera centre
 // (dir00 = pixel00_loc - center, evaluated in double on the host) so that FP32 keeps
 // sub-pixel accuracy when the camera sits hundreds of units from the origin.
+template <bool LITE = false>
 __device__ __forceinline__ Ray camera_ray(const DevScene& S, int i, int j, const Rng& rng) {
     float4 u = rng.draw(0, RS_CAMERA);
     float fx = (float)i + (u.x - 0.5f), fy = (float)j + (u.y - 0.5f);
@@ -800,7 +805,7 @@ __device__ __forceinline__ Ray camera_ray(const DevScene& S, int i, int j, const
     Ray r;
     r.o = v3(S.center);
     r.time = u.z;
-    if (S.defocus) {
+    if (!LITE && S.defocus) {
         // random_in_unit_disk (vec3.h:135-142): rejection sampling, two candidates per draw
         float px = 0.0f, py = 0.0f;
         for (uint32_t attempt = 0;; attempt++) {

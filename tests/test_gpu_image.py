@@ -180,3 +180,20 @@ def test_both_kernel_versions_render_the_same_bits(built, scene_of):
         c.close()
     assert np.array_equal(frames[0], frames[1])
     assert np.array_equal(frames[0], frames[2])   # the wavefront pipeline too
+
+
+def test_lite_kernel_instance_renders_the_same_bits(ctx, scene_of):
+    """Scenes without triangles, point lights and defocus run an instance of the kernel compiled
+    without those features (smaller, faster); it must be the same function of the samples."""
+    import os
+
+    ctx.upload(scene_of("final"))
+    bind(ctx, 200, 112)
+    ctx.render(200, 112, 6, seed=4)
+    lite = accum_of(ctx)
+    os.environ["RT_B200_NO_LITE"] = "1"
+    try:
+        ctx.render(200, 112, 6, seed=4)
+    finally:
+        os.environ.pop("RT_B200_NO_LITE", None)
+    assert np.array_equal(lite, accum_of(ctx))
