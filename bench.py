@@ -388,6 +388,16 @@ def run_b200(args):
             "device_stats": {k: st[k] for k in ("regs_per_thread", "blocks", "threads_per_block", "bvh_nodes", "bvh_depth", "nonfinite_samples",
                                                 "local_bytes_per_thread")},
             "ms_render_only": ms_kernels / args.steps,
+            # active lanes per warp-level iteration of each phase of the megakernel (counted pass)
+            "lane_occupancy": {
+                "node_step_working": st["desc_lanes"] / max(1, st["desc_iters"]),
+                "node_step_holding_a_ray": st["desc_trav_lanes"] / max(1, st["desc_iters"]),
+                "leaf_visit": st["leaf_lanes"] / max(1, st["leaf_iters"]),
+                "shade_phase": st["shade_lanes"] / max(1, st["shade_iters"]),
+                "node_steps_per_ray": st["node_visits"] / max(1, st["rays"]),
+                "leaf_visits_per_ray": st["leaf_lanes"] / max(1, st["rays"]),
+                "shade_phases": st["shade_iters"], "node_iters": st["desc_iters"], "leaf_iters": st["leaf_iters"],
+            },
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -252,6 +252,12 @@ typedef struct rt_stats {
     uint32_t regs_per_thread;
     uint32_t threads_per_block, blocks;
     uint32_t local_bytes_per_thread;
+    /* lane occupancy of the megakernel's phases (RT_FLAG_STATS): warp-level iterations and the
+     * lanes that did work in them -- desc = one BVH node step, leaf = one leaf visit, shade = one
+     * shade phase; desc_trav_lanes = lanes holding a ray during a node step (working or waiting) */
+    uint64_t desc_iters, desc_lanes, desc_trav_lanes;
+    uint64_t leaf_iters, leaf_lanes;
+    uint64_t shade_iters, shade_lanes;
 } rt_stats;
 
 /* Create a context on CUDA device `device_ids[0]` (n_devices must be 1: this

@@ -116,6 +116,8 @@ class rt_stats(C.Structure):
         ("fp64_sphere_tests", C.c_uint64), ("nonfinite_samples", C.c_uint64), ("kernel_launches", C.c_uint32),
         ("bvh_nodes", C.c_uint32), ("bvh_depth", C.c_uint32), ("bvh_leaves", C.c_uint32), ("regs_per_thread", C.c_uint32),
         ("threads_per_block", C.c_uint32), ("blocks", C.c_uint32), ("local_bytes_per_thread", C.c_uint32),
+        ("desc_iters", C.c_uint64), ("desc_lanes", C.c_uint64), ("desc_trav_lanes", C.c_uint64), ("leaf_iters", C.c_uint64),
+        ("leaf_lanes", C.c_uint64), ("shade_iters", C.c_uint64), ("shade_lanes", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:

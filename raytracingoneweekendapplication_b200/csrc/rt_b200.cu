@@ -310,7 +310,15 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __g
                     const unsigned dmask = __ballot_sync(0xffffffffu, descending);
                     if (dmask == 0u) break;
                     if (kDescendDiv > 0 && kDescendDiv * __popc(dmask) <= __popc(__ballot_sync(0xffffffffu, state == LANE_TRAVERSE))) break;
+                    if (STATS) {
+                        const unsigned tmask = __ballot_sync(0xffffffffu, state == LANE_TRAVERSE);
+                        if (lane == 0) { st.desc_iters++; st.desc_lanes += __popc(dmask); st.desc_trav_lanes += __popc(tmask); }
+                    }
                     if (descending) tr.interior<STATS>(S, rc, 0.001f, stack, &st, &overflow);
+                }
+                if (STATS) {
+                    const unsigned lmask = __ballot_sync(0xffffffffu, state == LANE_TRAVERSE && tr.cur < 0 && !tr.done());
+                    if (lane == 0 && lmask) { st.leaf_iters++; st.leaf_lanes += __popc(lmask); }
                 }
                 if (state == LANE_TRAVERSE && tr.cur < 0) {
                     if (!tr.done()) tr.leaf<STATS, LITE>(S, ray, rc, 0.001f, origin_prim, stack, &st);
@@ -322,6 +330,10 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __g
         }
 
         // ---- 3. shade phase: Camera.txt:203-238 for the lanes whose traversal finished ------------
+        if (STATS) {
+            const unsigned smask = __ballot_sync(0xffffffffu, state == LANE_SHADE);
+            if (lane == 0) { st.shade_iters++; st.shade_lanes += __popc(smask); }
+        }
         if (state == LANE_SHADE) {
             Hit hit = tr.hit;
             int medium = -1;
@@ -1325,6 +1337,13 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
         ctx->stats.boundary_tests = h.boundary_tests;
         ctx->stats.fp64_sphere_tests = h.fp64_sphere;
         ctx->stats.nonfinite_samples = h.nonfinite;
+        ctx->stats.desc_iters = h.desc_iters;
+        ctx->stats.desc_lanes = h.desc_lanes;
+        ctx->stats.desc_trav_lanes = h.desc_trav_lanes;
+        ctx->stats.leaf_iters = h.leaf_iters;
+        ctx->stats.leaf_lanes = h.leaf_lanes;
+        ctx->stats.shade_iters = h.shade_iters;
+        ctx->stats.shade_lanes = h.shade_lanes;
     }
     return RT_OK;
 }

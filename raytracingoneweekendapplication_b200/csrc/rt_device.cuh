@@ -100,6 +100,8 @@ struct DevScene {
 struct Stats {
     unsigned long long rays, node_visits, box_tests, sphere_tests, quad_tests, tri_tests, medium_queries,
         boundary_tests, fp64_sphere, nonfinite, samples;
+    // lane occupancy of render_kernel_v2's phases, counted per warp-level iteration (lane 0 adds)
+    unsigned long long desc_iters, desc_lanes, desc_trav_lanes, leaf_iters, leaf_lanes, shade_iters, shade_lanes;
 };
 
 // ---------------------------------------------------------------------------------
