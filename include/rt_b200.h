@@ -308,6 +308,15 @@ int rt_render_aov(rt_ctx* ctx, int32_t width, int32_t height,
 int rt_accum_buffer(rt_ctx* ctx, void** device_ptr, size_t* bytes);
 int rt_bind_accum(rt_ctx* ctx, void* device_ptr, size_t bytes, int32_t width, int32_t height);
 
+/* Checkpoint / resume (replaces nothing in the reference, which restarts from scratch:
+ * Camera.txt:65-93 keeps its sums in a local `color` per pixel).  rt_accum_download copies the
+ * raw accumulation buffer (width*height*4 uint64) to the host; rt_accum_upload allocates a
+ * width x height frame if needed and restores it.  Rendering on with RT_FLAG_ACCUMULATE and
+ * spp_begin = the number of samples already in the buffer gives a frame bit-identical to an
+ * uninterrupted render of the same total. */
+int rt_accum_download(rt_ctx* ctx, uint64_t* host, size_t bytes);
+int rt_accum_upload(rt_ctx* ctx, const uint64_t* host, size_t bytes, int32_t width, int32_t height);
+
 int rt_get_stats(rt_ctx* ctx, rt_stats* out);
 
 /* sizeof() of the ABI structs as this library was compiled, so that a foreign-language

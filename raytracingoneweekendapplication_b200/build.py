@@ -47,7 +47,7 @@ def build_host(force: bool = False) -> str:
     out = os.path.join(PKG, "libscenes_b200.so")
     host = os.path.join(PKG, "host")
     inc = ["-I" + os.path.join(ROOT, "include"), "-I" + host, "-I" + os.path.join(ROOT, "scenes")]
-    srcs = [os.path.join(host, "rtow_host.h"), os.path.join(host, "png_write.h"), os.path.join(host, "host_rng.h"),
+    srcs = [os.path.join(host, "rtow_host.h"), os.path.join(host, "png_write.h"), os.path.join(host, "frame_io.h"), os.path.join(host, "host_rng.h"),
             os.path.join(ROOT, "scenes", "scenes.h"), os.path.join(ROOT, "scenes", "scenes_capi.cpp"),
             os.path.join(ROOT, "include", "rt_b200.h")]
     if force or _newer(out, srcs):

@@ -127,7 +127,7 @@ class rt_stats(C.Structure):
 EXPORTED_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_upload_scene", "rt_render", "rt_sync", "rt_download", "rt_render_aov",
     "rt_accum_buffer", "rt_bind_accum", "rt_get_stats", "rt_measure_fp32_peak", "rt_probe_texture", "rt_probe_scatter",
-    "rt_probe_hit", "rt_struct_size",
+    "rt_probe_hit", "rt_struct_size", "rt_accum_download", "rt_accum_upload",
 ]
 
 ABI_STRUCTS = [rt_scene_desc, rt_render_params, rt_stats, rt_sphere, rt_quad, rt_triangle, rt_medium, rt_material, rt_texture,
@@ -176,6 +176,8 @@ def load() -> C.CDLL:
     lib.rt_accum_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.rt_bind_accum.argtypes = [vp, vp, C.c_size_t, i32, i32]
     lib.rt_get_stats.argtypes = [vp, C.POINTER(rt_stats)]
+    lib.rt_accum_download.argtypes = [vp, vp, C.c_size_t]
+    lib.rt_accum_upload.argtypes = [vp, vp, C.c_size_t, i32, i32]
     lib.rt_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.rt_probe_texture.argtypes = [vp, i32, i32, vp, vp]
     lib.rt_probe_scatter.argtypes = [vp, i32, i32, vp, vp, vp]
@@ -211,6 +213,12 @@ def load_scenes() -> C.CDLL:
     s.rtsc_free.argtypes = [C.c_void_p]
     s.rtsc_free.restype = None
     s.rtsc_render_png.argtypes = [C.c_char_p, C.c_uint, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]
+    s.rtsc_render_resumable.argtypes = [C.c_char_p, C.c_uint, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p,
+                                        C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    s.rtsc_write_exr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+    s.rtsc_write_pfm.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+    s.rtsc_scene_hash.argtypes = [C.c_void_p]
+    s.rtsc_scene_hash.restype = C.c_uint64
     _scenes = s
     return s
 
@@ -326,6 +334,18 @@ class Context:
     def bind_accum(self, device_ptr: Optional[int], nbytes: int, width: int, height: int) -> None:
         self._check(self.lib.rt_bind_accum(self._h, device_ptr, nbytes, width, height))
         self.width, self.height = width, height
+
+    def accum_download(self) -> np.ndarray:
+        """The raw frame sums (H, W, 4) uint64: R, G, B in 2^-28 units and the dropped-sample count."""
+        out = np.empty((self.height, self.width, 4), dtype=np.uint64)
+        self._check(self.lib.rt_accum_download(self._h, out.ctypes.data, out.nbytes))
+        return out
+
+    def accum_upload(self, sums: np.ndarray) -> None:
+        sums = np.ascontiguousarray(sums, dtype=np.uint64)
+        h, w = sums.shape[0], sums.shape[1]
+        self._check(self.lib.rt_accum_upload(self._h, sums.ctypes.data, sums.nbytes, w, h))
+        self.width, self.height = w, h
 
     def stats(self) -> dict:
         st = rt_stats()

@@ -1131,6 +1131,34 @@ extern "C" int rt_accum_buffer(rt_ctx* ctx, void** device_ptr, size_t* bytes) {
     return RT_OK;
 }
 
+// Checkpoint / resume of a progressive render: the frame so far IS the
+// accumulation buffer (integer sums), so a raw copy of it plus the index of the next sample is a
+// complete checkpoint, and a resumed render is bit-identical to an uninterrupted one.
+extern "C" int rt_accum_download(rt_ctx* ctx, uint64_t* host, size_t bytes) {
+    if (!ctx || !host) return RT_ERR_INVALID;
+    if (!ctx->accum) return fail(ctx, RT_ERR_STATE, "rt_accum_download: nothing rendered or bound yet");
+    if (bytes < ctx->accum_bytes) return fail(ctx, RT_ERR_INVALID, "rt_accum_download: need %zu bytes, got %zu", ctx->accum_bytes, bytes);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaDeviceSynchronize());
+    ctx->pending_async = false;
+    CU(ctx, cudaMemcpy(host, ctx->accum, ctx->accum_bytes, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+extern "C" int rt_accum_upload(rt_ctx* ctx, const uint64_t* host, size_t bytes, int32_t width, int32_t height) {
+    if (!ctx || !host) return RT_ERR_INVALID;
+    if (width <= 0 || height <= 0 || (long long)width * height >= (1ll << 31)) return fail(ctx, RT_ERR_INVALID, "rt_accum_upload: bad frame size %dx%d", width, height);
+    const size_t need = (size_t)width * height * 4 * sizeof(unsigned long long);
+    if (bytes != need) return fail(ctx, RT_ERR_INVALID, "rt_accum_upload: a %dx%d frame is %zu bytes, got %zu", width, height, need, bytes);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaDeviceSynchronize());
+    ctx->pending_async = false;
+    int rc = ensure_accum(ctx, width, height);
+    if (rc != RT_OK) return rc;
+    CU(ctx, cudaMemcpy(ctx->accum, host, need, cudaMemcpyHostToDevice));
+    return RT_OK;
+}
+
 extern "C" int rt_sync(rt_ctx* ctx) {
     if (!ctx) return RT_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));

@@ -70,4 +70,35 @@ int rtsc_render_png(const char* name, unsigned seed, const char* asset_dir, int 
     return 0;
 }
 
+// The same call with the download-side additions: a checkpoint file, an
+// orderly stop after `stop_after_spp` samples, and a linear-radiance output (.exr / .pfm).
+// Reports how many samples the frame holds and how many of them came from the checkpoint.
+int rtsc_render_resumable(const char* name, unsigned seed, const char* asset_dir, int width, int height, int spp, int depth,
+                          const char* out_png, const char* checkpoint, int checkpoint_every_spp, int stop_after_spp,
+                          const char* linear_out, int* spp_done, int* spp_resumed) {
+    scene_config cfg;
+    if (asset_dir) cfg.asset_dir = asset_dir;
+    hittable_list world;
+    camera cam;
+    std::vector<point_light> lights;
+    if (!build_scene(name, seed, world, cam, lights, cfg)) return 1;
+    if (width > 0 && height > 0) { cam.image_width = width; cam.aspect_ratio = double(width) / double(height); }
+    if (spp > 0) cam.samples_per_pixel = spp;
+    if (depth > 0) cam.max_depth = depth;
+    cam.image_name = out_png;
+    if (checkpoint) cam.checkpoint_path = checkpoint;
+    cam.checkpoint_every_spp = checkpoint_every_spp;
+    cam.stop_after_spp = stop_after_spp;
+    if (linear_out) cam.linear_name = linear_out;
+    cam.render(world, lights);
+    if (spp_done) *spp_done = cam.last_spp_done;
+    if (spp_resumed) *spp_resumed = cam.last_spp_resumed;
+    return 0;
+}
+
+// The writers on their own (CPU tests): frame of w*h*3 floats -> file.
+int rtsc_write_exr(const char* path, int w, int h, const float* rgb) { return rtb200::write_exr(path, w, h, rgb) ? 0 : 1; }
+int rtsc_write_pfm(const char* path, int w, int h, const float* rgb) { return rtb200::write_pfm(path, w, h, rgb) ? 0 : 1; }
+uint64_t rtsc_scene_hash(const rtsc_scene* s) { return s ? s->fs.hash() : 0; }
+
 }  // extern "C"
