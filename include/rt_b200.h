@@ -258,6 +258,10 @@ typedef struct rt_stats {
     uint64_t desc_iters, desc_lanes, desc_trav_lanes;
     uint64_t leaf_iters, leaf_lanes;
     uint64_t shade_iters, shade_lanes;
+    /* shape of a ray's traversal (RT_FLAG_STATS): histograms of the node steps before the first
+     * leaf visit [0,64), between two leaf visits [64,128), after the last one [128,192) (last bin
+     * of each = that many or more), and of the leaf visits per ray [192,208) */
+    uint64_t trav_hist[208];
 } rt_stats;
 
 /* Create a context on CUDA device `device_ids[0]` (n_devices must be 1: this

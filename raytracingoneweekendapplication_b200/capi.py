@@ -118,10 +118,11 @@ class rt_stats(C.Structure):
         ("threads_per_block", C.c_uint32), ("blocks", C.c_uint32), ("local_bytes_per_thread", C.c_uint32),
         ("desc_iters", C.c_uint64), ("desc_lanes", C.c_uint64), ("desc_trav_lanes", C.c_uint64), ("leaf_iters", C.c_uint64),
         ("leaf_lanes", C.c_uint64), ("shade_iters", C.c_uint64), ("shade_lanes", C.c_uint64),
+        ("trav_hist", C.c_uint64 * 208),
     ]
 
     def as_dict(self) -> dict:
-        return {name: getattr(self, name) for name, _ in self._fields_}
+        return {name: (list(getattr(self, name)) if name == "trav_hist" else getattr(self, name)) for name, _ in self._fields_}
 
 
 EXPORTED_SYMBOLS = [

@@ -214,6 +214,10 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Dev
 #ifndef RT_DESCEND_DIV
 #define RT_DESCEND_DIV 0
 #endif
+// STATS only: histograms of the shape of a ray's traversal, written behind the Stats block --
+// node steps before the first leaf [0,64), between two leaf visits [64,128), after the last
+// leaf (or of a ray that reaches none) [128,192), and leaf visits per ray [192,208)
+constexpr int kTravHistBins = 208;
 constexpr int kTravThreshold = RT_TRAV_THRESHOLD;
 constexpr int kDescendDiv = RT_DESCEND_DIV;
 enum : int { LANE_IDLE = 0, LANE_TRAVERSE = 1, LANE_SHADE = 2 };
@@ -251,6 +255,8 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __g
     tr.hit.prim = PRIM_NONE;
     tr.hit.u = tr.hit.v = 0;
     const float kInf = __int_as_float(0x7f800000);
+    unsigned seg_steps = 0, n_leaf = 0;  // STATS: shape of the current ray's traversal
+    unsigned long long* hist = reinterpret_cast<unsigned long long*>(gstats + 1);
 
     while (true) {
         // ---- 1. idle lanes take the next (pixel, sample) pairs of the pool -----------------------
@@ -288,7 +294,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __g
                     origin_prim = PRIM_NONE;
                     tr.init(S, kInf);
                     state = tr.done() ? LANE_SHADE : LANE_TRAVERSE;
-                    if (STATS) { st.samples++; st.rays++; }
+                    if (STATS) { st.samples++; st.rays++; seg_steps = n_leaf = 0; }
                 }
             }
             pool_pos += min((unsigned)__popc(needy), pool_size - pool_pos);
@@ -314,14 +320,34 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __g
                         const unsigned tmask = __ballot_sync(0xffffffffu, state == LANE_TRAVERSE);
                         if (lane == 0) { st.desc_iters++; st.desc_lanes += __popc(dmask); st.desc_trav_lanes += __popc(tmask); }
                     }
-                    if (descending) tr.interior<STATS>(S, rc, 0.001f, stack, &st, &overflow);
+                    if (descending) {
+                        tr.interior<STATS>(S, rc, 0.001f, stack, &st, &overflow);
+                        if (STATS) {
+                            seg_steps++;
+                            if (tr.done()) {
+                                atomicAdd(hist + 128 + min(seg_steps, 63u), 1ull);
+                                atomicAdd(hist + 192 + min(n_leaf, 15u), 1ull);
+                            }
+                        }
+                    }
                 }
                 if (STATS) {
                     const unsigned lmask = __ballot_sync(0xffffffffu, state == LANE_TRAVERSE && tr.cur < 0 && !tr.done());
                     if (lane == 0 && lmask) { st.leaf_iters++; st.leaf_lanes += __popc(lmask); }
                 }
                 if (state == LANE_TRAVERSE && tr.cur < 0) {
-                    if (!tr.done()) tr.leaf<STATS, LITE>(S, ray, rc, 0.001f, origin_prim, stack, &st);
+                    if (!tr.done()) {
+                        tr.leaf<STATS, LITE>(S, ray, rc, 0.001f, origin_prim, stack, &st);
+                        if (STATS) {
+                            atomicAdd(hist + (n_leaf ? 64 : 0) + min(seg_steps, 63u), 1ull);
+                            n_leaf++;
+                            seg_steps = 0;
+                            if (tr.done()) {
+                                atomicAdd(hist + 128, 1ull);
+                                atomicAdd(hist + 192 + min(n_leaf, 15u), 1ull);
+                            }
+                        }
+                    }
                     if (tr.done()) state = LANE_SHADE;
                 }
                 const unsigned active = __ballot_sync(0xffffffffu, state == LANE_TRAVERSE);
@@ -389,7 +415,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __g
             } else {
                 tr.init(S, kInf);
                 state = tr.done() ? LANE_SHADE : LANE_TRAVERSE;
-                if (STATS) st.rays++;
+                if (STATS) { st.rays++; seg_steps = n_leaf = 0; }
             }
         }
     }
@@ -630,7 +656,7 @@ extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
     CU(ctx, cudaEventCreate(&ctx->ev0));
     CU(ctx, cudaEventCreate(&ctx->ev1));
     CU(ctx, cudaMalloc(&ctx->counters, 4 * sizeof(unsigned long long)));
-    CU(ctx, cudaMalloc(&ctx->dstats, sizeof(Stats)));
+    CU(ctx, cudaMalloc(&ctx->dstats, sizeof(Stats) + kTravHistBins * sizeof(unsigned long long)));
     // local-memory traversal stacks live in L1: prefer L1 over shared memory
     cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -1307,7 +1333,7 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
 
     if (!(p->flags & RT_FLAG_ACCUMULATE)) CU(ctx, cudaMemsetAsync(ctx->accum, 0, (size_t)p->width * p->height * 32, stream));
     CU(ctx, cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), stream));
-    if (stats) CU(ctx, cudaMemsetAsync(ctx->dstats, 0, sizeof(Stats), stream));
+    if (stats) CU(ctx, cudaMemsetAsync(ctx->dstats, 0, sizeof(Stats) + kTravHistBins * sizeof(unsigned long long), stream));
     const bool async = (p->flags & RT_FLAG_ASYNC) != 0;
     if (!async) CU(ctx, cudaEventRecord(ctx->ev0, stream));
     ctx->stats.kernel_launches = 0;
@@ -1321,9 +1347,18 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
         } else {
             // LITE: no triangles, no point lights, no defocus blur in this scene (see hit_prim)
             const bool lite = ctx->scene_lite && !getenv("RT_B200_NO_LITE");
+            // RT_B200_DUMMY_SMEM: unused dynamic shared memory per block, to measure what giving up
+            // that much L1 would cost (tuning experiment)
+            size_t dummy = 0;
+            if (const char* e = getenv("RT_B200_DUMMY_SMEM")) {
+                dummy = (size_t)atoi(e);
+                int pct = (int)std::min<size_t>(100, (100 * 3 * (dummy + 1024) + 233471) / 233472);
+                cudaFuncSetAttribute(render_kernel_v2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+                cudaFuncSetAttribute(render_kernel_v2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            }
             if (stats) render_kernel_v2<true, false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
-            else if (lite) render_kernel_v2<false, true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
-            else render_kernel_v2<false, false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            else if (lite) render_kernel_v2<false, true><<<grid, 256, dummy, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            else render_kernel_v2<false, false><<<grid, 256, dummy, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
         }
         CU(ctx, cudaGetLastError());
         if (ctx->kernel_version != 3) ctx->stats.kernel_launches = 1;
@@ -1372,6 +1407,7 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
         ctx->stats.leaf_lanes = h.leaf_lanes;
         ctx->stats.shade_iters = h.shade_iters;
         ctx->stats.shade_lanes = h.shade_lanes;
+        CU(ctx, cudaMemcpy(ctx->stats.trav_hist, ctx->dstats + 1, sizeof ctx->stats.trav_hist, cudaMemcpyDeviceToHost));
     }
     return RT_OK;
 }
