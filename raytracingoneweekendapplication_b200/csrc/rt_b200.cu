@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "bvh_build.h"
+#include "prim_derive.h"
 #include "rt_b200.h"
 #include "rt_device.cuh"
 #include "rt_wavefront.cuh"
@@ -708,38 +709,19 @@ extern "C" const char* rt_last_error(const rt_ctx* ctx) { return ctx ? ctx->erro
 // ---------------------------------------------------------------------------------
 namespace {
 
-struct D3 {
-    double x, y, z;
-};
-inline D3 d3(const double* p) { return D3{p[0], p[1], p[2]}; }
-inline D3 operator+(D3 a, D3 b) { return D3{a.x + b.x, a.y + b.y, a.z + b.z}; }
-inline D3 operator-(D3 a, D3 b) { return D3{a.x - b.x, a.y - b.y, a.z - b.z}; }
-inline D3 operator*(double s, D3 a) { return D3{s * a.x, s * a.y, s * a.z}; }
-inline double ddot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-inline D3 dcross(D3 a, D3 b) { return D3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
-inline D3 dunit(D3 a) { return (1.0 / std::sqrt(ddot(a, a))) * a; }
-
-inline D3 xf_point(const rt_xform* x, D3 p) {
-    if (!x) return p;
-    return D3{x->r[0] * p.x + x->r[1] * p.y + x->r[2] * p.z + x->t[0], x->r[3] * p.x + x->r[4] * p.y + x->r[5] * p.z + x->t[1],
-              x->r[6] * p.x + x->r[7] * p.y + x->r[8] * p.z + x->t[2]};
-}
-inline D3 xf_dir(const rt_xform* x, D3 d) {
-    if (!x) return d;
-    return D3{x->r[0] * d.x + x->r[1] * d.y + x->r[2] * d.z, x->r[3] * d.x + x->r[4] * d.y + x->r[5] * d.z,
-              x->r[6] * d.x + x->r[7] * d.y + x->r[8] * d.z};
-}
-
-struct BakedPrim {
-    uint32_t dev_type;
-    int src_type, src_index;
-    int prim_id;  // canonical id (-1 for boundaries)
-    // world-space geometry in double
-    D3 a, b, c;   // sphere: c0, cvec, -; quad: Q, u, v; triangle: p0, p1, p2
-    double radius;
-    int material, xform;
-    float uv[6];
-};
+using rtprep::BakedPrim;
+using rtprep::D3;
+using rtprep::d3;
+using rtprep::dcross;
+using rtprep::ddot;
+using rtprep::dunit;
+using rtprep::xf_dir;
+using rtprep::xf_point;
+using rtprep::operator+;
+using rtprep::operator-;
+using rtprep::operator*;
+static_assert((uint32_t)rtprep::PREP_SPHERE == (uint32_t)PT_SPHERE && (uint32_t)rtprep::PREP_MSPHERE == (uint32_t)PT_MSPHERE &&
+              (uint32_t)rtprep::PREP_QUAD == (uint32_t)PT_QUAD && (uint32_t)rtprep::PREP_TRI == (uint32_t)PT_TRI, "primitive type codes");
 
 bool texture_needs_uv(const rt_scene_desc* sc, int tex, int depth = 0) {
     if (tex < 0 || tex >= sc->n_textures || depth > 16) return false;
@@ -747,12 +729,6 @@ bool texture_needs_uv(const rt_scene_desc* sc, int tex, int depth = 0) {
     if (t.type == RT_TEX_IMAGE || t.type == RT_TEX_CHECKER_TRIANGLE) return true;
     if (t.type == RT_TEX_CHECKER) return texture_needs_uv(sc, t.even, depth + 1) || texture_needs_uv(sc, t.odd, depth + 1);
     return false;
-}
-
-inline float __int_as_float_host(int v) {
-    float f;
-    std::memcpy(&f, &v, 4);
-    return f;
 }
 
 }  // namespace
@@ -855,66 +831,12 @@ extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
     // ---- bake instance transforms, build per-primitive bounds -----------------------
     std::vector<BakedPrim> baked;
     baked.reserve((size_t)sc->n_world + sc->n_boundary_refs);
-    auto bake = [&](const rt_prim_ref& r, int prim_id) {
-        BakedPrim b{};
-        b.src_type = r.type;
-        b.src_index = r.index;
-        b.prim_id = prim_id;
-        if (r.type == RT_PRIM_SPHERE) {
-            const rt_sphere& s = sc->spheres[r.index];
-            const rt_xform* x = s.xform >= 0 ? &sc->xforms[s.xform] : nullptr;
-            b.a = xf_point(x, d3(s.center0));
-            b.b = xf_dir(x, d3(s.center_vec));
-            b.radius = s.radius;
-            b.material = s.material;
-            b.xform = s.xform;
-            bool moving = s.center_vec[0] != 0 || s.center_vec[1] != 0 || s.center_vec[2] != 0;
-            b.dev_type = moving ? PT_MSPHERE : PT_SPHERE;
-        } else if (r.type == RT_PRIM_QUAD) {
-            const rt_quad& q = sc->quads[r.index];
-            const rt_xform* x = q.xform >= 0 ? &sc->xforms[q.xform] : nullptr;
-            b.a = xf_point(x, d3(q.Q));
-            b.b = xf_dir(x, d3(q.u));
-            b.c = xf_dir(x, d3(q.v));
-            b.material = q.material;
-            b.xform = q.xform;
-            b.dev_type = PT_QUAD;
-        } else {
-            const rt_triangle& t = sc->triangles[r.index];
-            const rt_xform* x = t.xform >= 0 ? &sc->xforms[t.xform] : nullptr;
-            b.a = xf_point(x, d3(t.p0));
-            b.b = xf_point(x, d3(t.p1));
-            b.c = xf_point(x, d3(t.p2));
-            b.material = t.material;
-            b.xform = t.xform;
-            b.uv[0] = t.uv0[0]; b.uv[1] = t.uv0[1]; b.uv[2] = t.uv1[0]; b.uv[3] = t.uv1[1]; b.uv[4] = t.uv2[0]; b.uv[5] = t.uv2[1];
-            b.dev_type = PT_TRI;
-        }
-        baked.push_back(b);
-    };
+    const rtprep::Sources src{sc->spheres, sc->quads, sc->triangles, sc->xforms};
+    auto bake = [&](const rt_prim_ref& r, int prim_id) { baked.push_back(rtprep::bake_prim(src, r, prim_id)); };
     for (int i = 0; i < sc->n_world; i++) bake(sc->world[i], i);
     for (int i = 0; i < sc->n_boundary_refs; i++) bake(sc->boundary_refs[i], -1);
 
-    auto prim_box = [&](const BakedPrim& b, rtbvh::Box& box) {
-        auto grow = [&](D3 p, double pad) {
-            float lo[3] = {(float)(p.x - pad), (float)(p.y - pad), (float)(p.z - pad)};
-            float hi[3] = {(float)(p.x + pad), (float)(p.y + pad), (float)(p.z + pad)};
-            // (float) rounds to nearest: step one ulp outward so that the box stays conservative
-            for (int k = 0; k < 3; k++) { lo[k] = std::nextafter(lo[k], -INFINITY); hi[k] = std::nextafter(hi[k], INFINITY); }
-            box.grow(lo);
-            box.grow(hi);
-        };
-        if (b.dev_type == PT_SPHERE) {
-            grow(b.a, b.radius);
-        } else if (b.dev_type == PT_MSPHERE) {
-            grow(b.a, b.radius);
-            grow(b.a + b.b, b.radius);
-        } else if (b.dev_type == PT_QUAD) {
-            grow(b.a, 0); grow(b.a + b.b, 0); grow(b.a + b.c, 0); grow(b.a + b.b + b.c, 0);
-        } else {
-            grow(b.a, 0); grow(b.b, 0); grow(b.c, 0);
-        }
-    };
+    auto prim_box = [&](const BakedPrim& b, rtbvh::Box& box) { rtprep::prim_bounds(b, box.lo, box.hi); };
 
     std::vector<rtbvh::Prim> prims((size_t)sc->n_world);
     for (int i = 0; i < sc->n_world; i++) {
@@ -938,42 +860,33 @@ extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
     std::vector<double> sph_d, msph_d, quad_d, tri_d;
     std::vector<int4> sph_sh, msph_sh, quad_sh;
     std::vector<uint32_t> boundary_packed((size_t)sc->n_boundary_refs);
+    auto f4 = [](rtprep::F4 v) { return make_float4(v.x, v.y, v.z, v.w); };
+    auto i4 = [](rtprep::I4 v) { return make_int4(v.x, v.y, v.z, v.w); };
     auto emit = [&](const BakedPrim& b) -> uint32_t {
         if (b.dev_type == PT_SPHERE) {
-            sph.push_back(make_float4((float)b.a.x, (float)b.a.y, (float)b.a.z, (float)b.radius));
-            sph_d.insert(sph_d.end(), {b.a.x, b.a.y, b.a.z, b.radius});
-            sph_sh.push_back(make_int4(b.material, b.xform, b.prim_id, 0));
+            const rtprep::SphereRec r = rtprep::make_sphere(b);
+            sph.push_back(f4(r.g));
+            sph_d.insert(sph_d.end(), r.d, r.d + 4);
+            sph_sh.push_back(i4(r.sh));
             return (PT_SPHERE << 28) | (uint32_t)(sph.size() - 1);
         } else if (b.dev_type == PT_MSPHERE) {
-            msph.push_back(make_float4((float)b.a.x, (float)b.a.y, (float)b.a.z, (float)b.radius));
-            msph.push_back(make_float4((float)b.b.x, (float)b.b.y, (float)b.b.z, 0.0f));
-            msph_d.insert(msph_d.end(), {b.a.x, b.a.y, b.a.z, b.radius, b.b.x, b.b.y, b.b.z, 0.0});
-            msph_sh.push_back(make_int4(b.material, b.xform, b.prim_id, 0));
+            const rtprep::MSphereRec r = rtprep::make_msphere(b);
+            msph.push_back(f4(r.g0));
+            msph.push_back(f4(r.g1));
+            msph_d.insert(msph_d.end(), r.d, r.d + 8);
+            msph_sh.push_back(i4(r.sh));
             return (PT_MSPHERE << 28) | (uint32_t)(msph_sh.size() - 1);
         } else if (b.dev_type == PT_QUAD) {
-            // quad.h:13-21: n = u x v, normal = unit(n), D = normal.Q, w = n / (n.n)
-            D3 n = dcross(b.b, b.c);
-            D3 normal = dunit(n);
-            double D = ddot(normal, b.a);
-            D3 w = (1.0 / ddot(n, n)) * n;
-            D3 A = dcross(b.c, w), B = dcross(w, b.b);  // alpha = A.(p-Q), beta = B.(p-Q)
-            double a0 = ddot(A, b.a), b0 = ddot(B, b.a);
-            quad.push_back(make_float4((float)normal.x, (float)normal.y, (float)normal.z, (float)D));
-            quad.push_back(make_float4((float)A.x, (float)A.y, (float)A.z, (float)a0));
-            quad.push_back(make_float4((float)B.x, (float)B.y, (float)B.z, (float)b0));
-            quad_d.insert(quad_d.end(), {normal.x, normal.y, normal.z, D, A.x, A.y, A.z, a0, B.x, B.y, B.z, b0});
-            quad_sh.push_back(make_int4(b.material, 0, b.prim_id, 0));
+            const rtprep::QuadRec r = rtprep::make_quad(b);
+            for (int k = 0; k < 3; k++) quad.push_back(f4(r.q[k]));
+            quad_d.insert(quad_d.end(), r.d, r.d + 12);
+            quad_sh.push_back(i4(r.sh));
             return (PT_QUAD << 28) | (uint32_t)(quad_sh.size() - 1);
         } else {
-            D3 e1 = b.b - b.a, e2 = b.c - b.a;
-            D3 normal = dunit(dcross(e1, e2));  // triangle.h:21-22
-            tri.push_back(make_float4((float)b.a.x, (float)b.a.y, (float)b.a.z, 0.0f));
-            tri.push_back(make_float4((float)e1.x, (float)e1.y, (float)e1.z, 0.0f));
-            tri.push_back(make_float4((float)e2.x, (float)e2.y, (float)e2.z, 0.0f));
-            tri_d.insert(tri_d.end(), {b.a.x, b.a.y, b.a.z, e1.x, e1.y, e1.z, e2.x, e2.y, e2.z});
-            tri_sh.push_back(make_float4((float)normal.x, (float)normal.y, (float)normal.z, __int_as_float_host(b.material)));
-            tri_sh.push_back(make_float4(b.uv[0], b.uv[1], b.uv[2], b.uv[3]));
-            tri_sh.push_back(make_float4(b.uv[4], b.uv[5], __int_as_float_host(b.prim_id), 0.0f));
+            const rtprep::TriRec r = rtprep::make_triangle(b);
+            for (int k = 0; k < 3; k++) tri.push_back(f4(r.t[k]));
+            tri_d.insert(tri_d.end(), r.d, r.d + 9);
+            for (int k = 0; k < 3; k++) tri_sh.push_back(f4(r.sh[k]));
             return (PT_TRI << 28) | (uint32_t)(tri_sh.size() / 3 - 1);
         }
     };
