@@ -262,6 +262,10 @@ typedef struct rt_stats {
      * leaf visit [0,64), between two leaf visits [64,128), after the last one [128,192) (last bin
      * of each = that many or more), and of the leaf visits per ray [192,208) */
     uint64_t trav_hist[208];
+    /* scene-upload path of the last rt_upload_scene: 1 = acceleration structure and device records
+     * built by CUDA kernels, with the device time of the build and of the raw-input copy */
+    uint32_t bvh_on_device, reserved_;
+    double device_build_ms, device_copy_in_ms;
 } rt_stats;
 
 /* Create a context on CUDA device `device_ids[0]` (n_devices must be 1: this
@@ -275,6 +279,15 @@ const char* rt_last_error(const rt_ctx* ctx);
  * transforms, builds the SAH BVH on the host, converts to the device layout and
  * uploads.  Replaces main.cpp:442 (bvh_node construction). */
 int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene);
+
+/* Which builder rt_upload_scene uses (replaces bvh.h:13-45 either way).
+ *   1 host:   transforms baked, binned-SAH BVH2 and device records built on the CPU (best tree)
+ *   2 device: raw arrays copied as they are; LBVH (Morton sort + radix tree) and device records
+ *             built by CUDA kernels: ~100x faster upload for million-primitive scenes, slower tree
+ *   0 auto:   device from 2^20 primitives up (environment RT_B200_BVH=host|device overrides at rt_create)
+ * Images do not depend on the choice (same records bit for bit, closest hit is tree-independent)
+ * except where two primitives are hit at exactly the same t. */
+int rt_set_bvh_builder(rt_ctx* ctx, int32_t mode);
 
 /* Runs the whole bounce loop (Camera.txt:65-93, 177-272) for this context's
  * shard of samples [spp_begin, spp_begin + samples_per_pixel) and adds the

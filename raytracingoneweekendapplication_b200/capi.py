@@ -119,6 +119,7 @@ class rt_stats(C.Structure):
         ("desc_iters", C.c_uint64), ("desc_lanes", C.c_uint64), ("desc_trav_lanes", C.c_uint64), ("leaf_iters", C.c_uint64),
         ("leaf_lanes", C.c_uint64), ("shade_iters", C.c_uint64), ("shade_lanes", C.c_uint64),
         ("trav_hist", C.c_uint64 * 208),
+        ("bvh_on_device", C.c_uint32), ("reserved_", C.c_uint32), ("device_build_ms", C.c_double), ("device_copy_in_ms", C.c_double),
     ]
 
     def as_dict(self) -> dict:
@@ -128,7 +129,7 @@ class rt_stats(C.Structure):
 EXPORTED_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_upload_scene", "rt_render", "rt_sync", "rt_download", "rt_render_aov",
     "rt_accum_buffer", "rt_bind_accum", "rt_get_stats", "rt_measure_fp32_peak", "rt_probe_texture", "rt_probe_scatter",
-    "rt_probe_hit", "rt_struct_size", "rt_accum_download", "rt_accum_upload",
+    "rt_probe_hit", "rt_struct_size", "rt_accum_download", "rt_accum_upload", "rt_set_bvh_builder",
 ]
 
 ABI_STRUCTS = [rt_scene_desc, rt_render_params, rt_stats, rt_sphere, rt_quad, rt_triangle, rt_medium, rt_material, rt_texture,
@@ -177,6 +178,7 @@ def load() -> C.CDLL:
     lib.rt_accum_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.rt_bind_accum.argtypes = [vp, vp, C.c_size_t, i32, i32]
     lib.rt_get_stats.argtypes = [vp, C.POINTER(rt_stats)]
+    lib.rt_set_bvh_builder.argtypes = [vp, i32]
     lib.rt_accum_download.argtypes = [vp, vp, C.c_size_t]
     lib.rt_accum_upload.argtypes = [vp, vp, C.c_size_t, i32, i32]
     lib.rt_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
@@ -281,6 +283,10 @@ class Context:
     def _check(self, rc: int):
         if rc != RT_OK:
             raise RtError(rc, self.lib.rt_last_error(self._h).decode())
+
+    def set_bvh_builder(self, mode: str) -> None:
+        """'auto' | 'host' (binned SAH on the CPU) | 'device' (LBVH in CUDA kernels) for the next upload."""
+        self._check(self.lib.rt_set_bvh_builder(self._h, {"auto": 0, "host": 1, "device": 2}[mode]))
 
     def upload(self, scene) -> None:
         if hasattr(scene, "desc_ptr"):          # capi.Scene or any object that keeps a description alive

@@ -23,6 +23,7 @@
 
 #include "bvh_build.h"
 #include "prim_derive.h"
+#include "bvh_device.cuh"
 #include "rt_b200.h"
 #include "rt_device.cuh"
 #include "rt_wavefront.cuh"
@@ -591,7 +592,18 @@ struct rt_ctx {
     int wf_blocks_per_sm[2] = {0, 0};
     int blocks_per_sm[2] = {0, 0};
     bool pending_async = false;
+    // scene-upload path: 0 auto (device LBVH from kDeviceBuildAuto primitives up), 1 host SAH, 2 device LBVH
+    int bvh_builder = 0;
+    unsigned char* scratch = nullptr;  // work space of the device build, reused across uploads
+    size_t scratch_cap = 0;
 };
+
+// From this many primitives on, RT_B200_BVH=auto builds on the device: the host SAH build costs
+// ~0.45 s per million triangles, the device path a few milliseconds, and the LBVH it produces
+// renders measurably slower per sample (numbers in DESIGN.md) -- above this size an upload is worth
+// more than 100 samples per pixel of a 1080p frame.
+constexpr int kDeviceBuildAuto = 1 << 20;
+constexpr int kDeviceBuildMin = 8;
 
 static int fail(rt_ctx* ctx, int code, const char* fmt, ...) {
     char buf[512];
@@ -613,6 +625,9 @@ static void free_scene(rt_ctx* ctx) { ctx->has_scene = false; }
 
 static void release_buffers(rt_ctx* ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_cap = 0;
     if (ctx->pool_mem) cudaFree(ctx->pool_mem);
     ctx->pool_mem = nullptr;
     ctx->pool = rtwf::Pool{};
@@ -664,6 +679,7 @@ extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
     cudaFuncSetAttribute(render_kernel_v2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    if (const char* bv = getenv("RT_B200_BVH")) ctx->bvh_builder = strcmp(bv, "host") == 0 ? 1 : (strcmp(bv, "device") == 0 ? 2 : 0);
     if (const char* kv = getenv("RT_B200_KERNEL")) ctx->kernel_version = strcmp(kv, "v1") == 0 ? 1 : (strcmp(kv, "wf") == 0 ? 3 : 2);
     cudaFuncSetAttribute(rtwf::wf_extend<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(rtwf::wf_extend<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -819,41 +835,49 @@ static void setup_camera(rt_ctx* ctx, int width, int height) {
     ctx->cam_h = height;
 }
 
-extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
-    if (!ctx) return RT_ERR_INVALID;
+// `too_deep` is set when the device-built tree is deeper than the traversal stack allows; the
+// caller then repeats the upload on the host path.
+static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_build, bool* too_deep) {
     auto t_begin = std::chrono::steady_clock::now();
-    int rc = validate_scene(ctx, sc);
-    if (rc != RT_OK) return rc;
-    CU(ctx, cudaSetDevice(ctx->device));
-    if (ctx->pending_async) { CU(ctx, cudaStreamSynchronize(ctx->stream)); ctx->pending_async = false; }
-    free_scene(ctx);
+    const rtprep::Sources src{sc->spheres, sc->quads, sc->triangles, sc->xforms};
+    size_t world_count[4] = {0, 0, 0, 0};  // device path: primitives of each device type the kernels will write
 
     // ---- bake instance transforms, build per-primitive bounds -----------------------
     std::vector<BakedPrim> baked;
-    baked.reserve((size_t)sc->n_world + sc->n_boundary_refs);
-    const rtprep::Sources src{sc->spheres, sc->quads, sc->triangles, sc->xforms};
-    auto bake = [&](const rt_prim_ref& r, int prim_id) { baked.push_back(rtprep::bake_prim(src, r, prim_id)); };
-    for (int i = 0; i < sc->n_world; i++) bake(sc->world[i], i);
-    for (int i = 0; i < sc->n_boundary_refs; i++) bake(sc->boundary_refs[i], -1);
-
-    auto prim_box = [&](const BakedPrim& b, rtbvh::Box& box) { rtprep::prim_bounds(b, box.lo, box.hi); };
-
-    std::vector<rtbvh::Prim> prims((size_t)sc->n_world);
-    for (int i = 0; i < sc->n_world; i++) {
-        rtbvh::Prim& p = prims[i];
-        prim_box(baked[i], p.box);
-        for (int k = 0; k < 3; k++) p.centroid[k] = 0.5f * (p.box.lo[k] + p.box.hi[k]);
-        p.type = baked[i].dev_type;
-        p.index = (uint32_t)i;
-        p.cost = baked[i].dev_type == PT_SPHERE ? 1.0f : (baked[i].dev_type == PT_MSPHERE ? 1.2f : 1.3f);
-    }
     rtbvh::Result bvh;
-    {
+    if (device_build) {
+        for (int i = 0; i < sc->n_world; i++) {
+            const rt_prim_ref r = sc->world[i];
+            uint32_t t = r.type == RT_PRIM_QUAD ? PT_QUAD : (r.type == RT_PRIM_TRIANGLE ? PT_TRI : PT_SPHERE);
+            if (r.type == RT_PRIM_SPHERE) {
+                const double* v = sc->spheres[r.index].center_vec;
+                if (v[0] != 0 || v[1] != 0 || v[2] != 0) t = PT_MSPHERE;
+            }
+            world_count[t]++;
+        }
+        baked.reserve((size_t)sc->n_boundary_refs);
+        for (int i = 0; i < sc->n_boundary_refs; i++) baked.push_back(rtprep::bake_prim(src, sc->boundary_refs[i], -1));
+    } else {
+        for (int k = 0; k < 4; k++) world_count[k] = 0;
+        baked.reserve((size_t)sc->n_world + sc->n_boundary_refs);
+        for (int i = 0; i < sc->n_world; i++) baked.push_back(rtprep::bake_prim(src, sc->world[i], i));
+        for (int i = 0; i < sc->n_boundary_refs; i++) baked.push_back(rtprep::bake_prim(src, sc->boundary_refs[i], -1));
+
+        std::vector<rtbvh::Prim> prims((size_t)sc->n_world);
+        for (int i = 0; i < sc->n_world; i++) {
+            rtbvh::Prim& p = prims[i];
+            rtprep::prim_bounds(baked[i], p.box.lo, p.box.hi);
+            for (int k = 0; k < 3; k++) p.centroid[k] = 0.5f * (p.box.lo[k] + p.box.hi[k]);
+            p.type = baked[i].dev_type;
+            p.index = (uint32_t)i;
+            p.cost = baked[i].dev_type == PT_SPHERE ? 1.0f : (baked[i].dev_type == PT_MSPHERE ? 1.2f : 1.3f);
+        }
         rtbvh::Tuning tune;  // RT_B200_MAX_LEAF / RT_B200_TRAV_COST: tuning experiments only
         if (const char* e = getenv("RT_B200_MAX_LEAF")) tune.max_leaf = std::max(1, std::min(8, atoi(e)));
         if (const char* e = getenv("RT_B200_TRAV_COST")) tune.trav_cost = (float)atof(e);
         rtbvh::build_bvh(prims, bvh, tune);
     }
+    const size_t first_boundary = device_build ? 0 : (size_t)sc->n_world;
 
     // ---- device arrays in leaf order, boundaries appended ------------------------------
     std::vector<float4> sph, msph, quad, tri, tri_sh;
@@ -868,30 +892,30 @@ extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
             sph.push_back(f4(r.g));
             sph_d.insert(sph_d.end(), r.d, r.d + 4);
             sph_sh.push_back(i4(r.sh));
-            return (PT_SPHERE << 28) | (uint32_t)(sph.size() - 1);
+            return (PT_SPHERE << 28) | (uint32_t)(world_count[PT_SPHERE] + sph.size() - 1);
         } else if (b.dev_type == PT_MSPHERE) {
             const rtprep::MSphereRec r = rtprep::make_msphere(b);
             msph.push_back(f4(r.g0));
             msph.push_back(f4(r.g1));
             msph_d.insert(msph_d.end(), r.d, r.d + 8);
             msph_sh.push_back(i4(r.sh));
-            return (PT_MSPHERE << 28) | (uint32_t)(msph_sh.size() - 1);
+            return (PT_MSPHERE << 28) | (uint32_t)(world_count[PT_MSPHERE] + msph_sh.size() - 1);
         } else if (b.dev_type == PT_QUAD) {
             const rtprep::QuadRec r = rtprep::make_quad(b);
             for (int k = 0; k < 3; k++) quad.push_back(f4(r.q[k]));
             quad_d.insert(quad_d.end(), r.d, r.d + 12);
             quad_sh.push_back(i4(r.sh));
-            return (PT_QUAD << 28) | (uint32_t)(quad_sh.size() - 1);
+            return (PT_QUAD << 28) | (uint32_t)(world_count[PT_QUAD] + quad_sh.size() - 1);
         } else {
             const rtprep::TriRec r = rtprep::make_triangle(b);
             for (int k = 0; k < 3; k++) tri.push_back(f4(r.t[k]));
             tri_d.insert(tri_d.end(), r.d, r.d + 9);
             for (int k = 0; k < 3; k++) tri_sh.push_back(f4(r.sh[k]));
-            return (PT_TRI << 28) | (uint32_t)(tri_sh.size() / 3 - 1);
+            return (PT_TRI << 28) | (uint32_t)(world_count[PT_TRI] + tri_sh.size() / 3 - 1);
         }
     };
     for (uint32_t id : bvh.order) emit(baked[id]);
-    for (int i = 0; i < sc->n_boundary_refs; i++) boundary_packed[i] = emit(baked[(size_t)sc->n_world + i]);
+    for (int i = 0; i < sc->n_boundary_refs; i++) boundary_packed[i] = emit(baked[first_boundary + i]);
 
     // ---- tables ---------------------------------------------------------------------------
     std::vector<DevMaterial> mats((size_t)sc->n_materials);
@@ -965,18 +989,35 @@ extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
 
     DevScene& S = ctx->scene;
     std::memset(&S, 0, sizeof S);
-    // ---- one arena, one copy -----------------------------------------------------------------
-    ArenaPlan plan;
-    std::vector<size_t> img_off((size_t)sc->n_images);
-    for (int i = 0; i < sc->n_images; i++) img_off[i] = plan.add((size_t)sc->images[i].width * sc->images[i].height * 3);
-    struct Block { const void* src; size_t bytes, off; const void** field; };
+    // ---- one arena.  Host path: everything is staged in pinned memory at its arena offset and moved
+    // with ONE copy.  Device path: the typed arrays and the nodes are written by kernels (`skip` bytes
+    // at the front of a block: the world primitives), only the tables and the boundary records that
+    // follow the world primitives are staged, compactly, and copied block by block.
+    ArenaPlan plan, stage;
+    std::vector<size_t> img_off((size_t)sc->n_images), img_stage((size_t)sc->n_images);
+    for (int i = 0; i < sc->n_images; i++) {
+        img_off[i] = plan.add((size_t)sc->images[i].width * sc->images[i].height * 3);
+        img_stage[i] = stage.add((size_t)sc->images[i].width * sc->images[i].height * 3);
+    }
+    struct Block { const void* src; size_t bytes, off, skip, stage_off; const void** field; };
     std::vector<Block> blocks;
-#define UP(vec, field) blocks.push_back(Block{vec.data(), vec.size() * sizeof(vec[0]), plan.add(vec.size() * sizeof(vec[0])), (const void**)&S.field});
-    UP(nodes, nodes) UP(sph, sph) UP(msph, msph) UP(quad, quad) UP(tri, tri) UP(sph_d, sph_d) UP(msph_d, msph_d) UP(quad_d, quad_d)
-    UP(tri_d, tri_d) UP(sph_sh, sph_sh) UP(msph_sh, msph_sh) UP(quad_sh, quad_sh) UP(tri_sh, tri_sh) UP(xrot, xrot) UP(media, media)
+    auto add_block = [&](const void* data, size_t bytes, size_t skip, const void** field) {
+        Block b{data, bytes, plan.add(skip + bytes), skip, 0, field};
+        b.stage_off = stage.add(bytes);
+        blocks.push_back(b);
+    };
+    const size_t node_skip = device_build ? (size_t)(sc->n_world - 1) * 64 : 0;
+#define UP(vec, field) add_block(vec.data(), vec.size() * sizeof(vec[0]), 0, (const void**)&S.field);
+#define UPW(vec, field, type, rec_bytes) add_block(vec.data(), vec.size() * sizeof(vec[0]), world_count[type] * (size_t)(rec_bytes), (const void**)&S.field);
+    add_block(nodes.data(), device_build ? 0 : nodes.size() * sizeof(float4), node_skip, (const void**)&S.nodes);
+    UPW(sph, sph, PT_SPHERE, 16) UPW(msph, msph, PT_MSPHERE, 32) UPW(quad, quad, PT_QUAD, 48) UPW(tri, tri, PT_TRI, 48)
+    UPW(sph_d, sph_d, PT_SPHERE, 32) UPW(msph_d, msph_d, PT_MSPHERE, 64) UPW(quad_d, quad_d, PT_QUAD, 96) UPW(tri_d, tri_d, PT_TRI, 72)
+    UPW(sph_sh, sph_sh, PT_SPHERE, 16) UPW(msph_sh, msph_sh, PT_MSPHERE, 16) UPW(quad_sh, quad_sh, PT_QUAD, 16) UPW(tri_sh, tri_sh, PT_TRI, 48)
+    UP(xrot, xrot) UP(media, media)
     UP(boundary_packed, boundary) UP(mats, mats) UP(texs, texs) UP(images, images) UP(perlin_vec, perlin_vec)
     UP(perlin_perm, perlin_perm) UP(lights, lights)
 #undef UP
+#undef UPW
     if (plan.size > ctx->arena_cap) {
         if (ctx->arena) cudaFree(ctx->arena);
         ctx->arena = nullptr;
@@ -985,38 +1026,102 @@ extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
         if (cudaMalloc(&ctx->arena, cap) != cudaSuccess) return fail(ctx, RT_ERR_NOMEM, "rt_upload_scene: cannot allocate %zu bytes of device memory", cap);
         ctx->arena_cap = cap;
     }
-    if (plan.size > ctx->staging_cap) {
+    const size_t stage_need = device_build ? stage.size : plan.size;
+    if (stage_need > ctx->staging_cap) {
         if (ctx->staging) cudaFreeHost(ctx->staging);
         ctx->staging = nullptr;
         ctx->staging_cap = 0;
-        size_t cap = plan.size + plan.size / 4;
+        size_t cap = stage_need + stage_need / 4;
         if (cudaHostAlloc(&ctx->staging, cap, cudaHostAllocDefault) != cudaSuccess)
             return fail(ctx, RT_ERR_NOMEM, "rt_upload_scene: cannot allocate %zu bytes of pinned host memory", cap);
         ctx->staging_cap = cap;
     }
     for (int i = 0; i < sc->n_images; i++) {
         images[i].rgb = ctx->arena + img_off[i];
-        std::memcpy(ctx->staging + img_off[i], sc->images[i].rgb, (size_t)sc->images[i].width * sc->images[i].height * 3);
+        std::memcpy(ctx->staging + (device_build ? img_stage[i] : img_off[i]), sc->images[i].rgb, (size_t)sc->images[i].width * sc->images[i].height * 3);
     }
     for (const Block& b : blocks) {
-        if (b.bytes) std::memcpy(ctx->staging + b.off, b.src, b.bytes);
+        if (b.bytes) std::memcpy(ctx->staging + (device_build ? b.stage_off : b.off), b.src, b.bytes);
         *b.field = ctx->arena + b.off;
     }
-    CU(ctx, cudaMemcpyAsync(ctx->arena, ctx->staging, plan.size, cudaMemcpyHostToDevice, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    S.root = bvh.root;
-    S.n_nodes = (int)bvh.nodes.size();
+    uint32_t n_nodes = (uint32_t)bvh.nodes.size(), depth = bvh.depth, leaves = bvh.leaves;
+    int root = bvh.root;
+    if (!device_build) {
+        CU(ctx, cudaMemcpyAsync(ctx->arena, ctx->staging, plan.size, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        for (int i = 0; i < sc->n_images; i++)
+            CU(ctx, cudaMemcpyAsync(ctx->arena + img_off[i], ctx->staging + img_stage[i], (size_t)sc->images[i].width * sc->images[i].height * 3,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+        for (const Block& b : blocks)
+            if (b.bytes) CU(ctx, cudaMemcpyAsync(ctx->arena + b.off + b.skip, ctx->staging + b.stage_off, b.bytes, cudaMemcpyHostToDevice, ctx->stream));
+        const rtlbvh::Layout L = rtlbvh::plan_scratch(sc);
+        if (L.total > ctx->scratch_cap) {
+            if (ctx->scratch) cudaFree(ctx->scratch);
+            ctx->scratch = nullptr;
+            ctx->scratch_cap = 0;
+            size_t cap = L.total + L.total / 8;
+            if (cudaMalloc(&ctx->scratch, cap) != cudaSuccess) return fail(ctx, RT_ERR_NOMEM, "rt_upload_scene: cannot allocate %zu bytes of build work space", cap);
+            ctx->scratch_cap = cap;
+        }
+        rtlbvh::Targets T;
+        T.nodes = (float4*)S.nodes;
+        T.sph = (float4*)S.sph; T.msph = (float4*)S.msph; T.quad = (float4*)S.quad; T.tri = (float4*)S.tri; T.tri_sh = (float4*)S.tri_sh;
+        T.sph_d = (double*)S.sph_d; T.msph_d = (double*)S.msph_d; T.quad_d = (double*)S.quad_d; T.tri_d = (double*)S.tri_d;
+        T.sph_sh = (int4*)S.sph_sh; T.msph_sh = (int4*)S.msph_sh; T.quad_sh = (int4*)S.quad_sh;
+        rtlbvh::BuildResult br;
+        CU(ctx, rtlbvh::build_on_device(sc, ctx->scratch, L, T, ctx->stream, br));
+        n_nodes = br.nodes;
+        depth = br.depth;
+        leaves = br.leaves;
+        root = 0;
+        ctx->stats.device_build_ms = br.ms_build + br.ms_emit;
+        ctx->stats.device_copy_in_ms = br.ms_copy_in;
+        if (depth >= (uint32_t)STACK_SIZE - 2) {
+            *too_deep = true;
+            return RT_OK;
+        }
+    }
+    ctx->stats.bvh_on_device = device_build ? 1 : 0;
+    S.root = root;
+    S.n_nodes = device_build ? sc->n_world - 1 : (int)bvh.nodes.size();
     S.n_world = sc->n_world;
     S.n_media = sc->n_media;
     S.n_lights = sc->n_lights;
     ctx->camera = sc->camera;
-    ctx->scene_lite = tri.empty() && sc->n_lights == 0 && !(sc->camera.defocus_angle > 0);
+    ctx->scene_lite = tri.empty() && world_count[PT_TRI] == 0 && sc->n_lights == 0 && !(sc->camera.defocus_angle > 0);
     ctx->cam_w = ctx->cam_h = 0;
     ctx->has_scene = true;
-    ctx->stats.bvh_nodes = (uint32_t)bvh.nodes.size();
-    ctx->stats.bvh_depth = bvh.depth;
-    ctx->stats.bvh_leaves = bvh.leaves;
+    ctx->stats.bvh_nodes = n_nodes;
+    ctx->stats.bvh_depth = depth;
+    ctx->stats.bvh_leaves = leaves;
     ctx->stats.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return RT_OK;
+}
+
+extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
+    if (!ctx) return RT_ERR_INVALID;
+    auto t_begin = std::chrono::steady_clock::now();
+    int rc = validate_scene(ctx, sc);
+    if (rc != RT_OK) return rc;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (ctx->pending_async) { CU(ctx, cudaStreamSynchronize(ctx->stream)); ctx->pending_async = false; }
+    free_scene(ctx);
+    // which path: host (bake + binned SAH on the CPU) or device (csrc/bvh_device.cuh)
+    const bool device_build = sc->n_world >= kDeviceBuildMin && (ctx->bvh_builder == 2 || (ctx->bvh_builder == 0 && sc->n_world >= kDeviceBuildAuto));
+    ctx->stats.device_build_ms = ctx->stats.device_copy_in_ms = 0;
+    bool too_deep = false;
+    rc = upload_scene_impl(ctx, sc, device_build, &too_deep);
+    if (rc == RT_OK && too_deep) rc = upload_scene_impl(ctx, sc, false, &too_deep);  // degenerate input: the SAH tree is shallow
+    if (rc == RT_OK) ctx->stats.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return rc;
+}
+
+// 0 auto, 1 host SAH, 2 device LBVH: which builder the next rt_upload_scene uses
+extern "C" int rt_set_bvh_builder(rt_ctx* ctx, int32_t mode) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (mode < 0 || mode > 2) return fail(ctx, RT_ERR_INVALID, "rt_set_bvh_builder: mode %d (0 auto, 1 host, 2 device)", mode);
+    ctx->bvh_builder = mode;
     return RT_OK;
 }
 

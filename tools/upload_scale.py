@@ -83,6 +83,8 @@ def main():
         d, keep = scene_desc(tris)
         t_gen = time.perf_counter() - t0
         ctx = capi.Context(0)
+        mode = os.environ.get("RT_B200_BVH", "host")
+        ctx.set_bvh_builder(mode)
         ups = []
         for _ in range(3):
             t0 = time.perf_counter()
@@ -100,7 +102,8 @@ def main():
                           "upload_ms_best": round(1e3 * min(ups), 1), "bvh_nodes": st["bvh_nodes"], "bvh_depth": st["bvh_depth"],
                           "render_ms": round(best, 2), "msamples_s": round(w * h * spp / best / 1e3, 1),
                           "primary_hit_fraction": round(float((aov["prim_id"] >= 0).mean()), 4),
-                          "builder": os.environ.get("RT_B200_BVH", "host-sah")}), flush=True)
+                          "builder": mode, "on_device": st["bvh_on_device"], "device_build_ms": round(st["device_build_ms"], 3),
+                          "device_copy_in_ms": round(st["device_copy_in_ms"], 3), "bvh_leaves": st["bvh_leaves"]}), flush=True)
         ctx.close()
 
 
