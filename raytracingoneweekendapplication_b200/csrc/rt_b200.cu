@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bvh_build.h"
@@ -594,6 +595,7 @@ struct rt_ctx {
     bool pending_async = false;
     // scene-upload path: 0 auto (device LBVH from kDeviceBuildAuto primitives up), 1 host SAH, 2 device LBVH
     int bvh_builder = 0;
+    size_t world_type_count[4] = {0, 0, 0, 0};  // primitives of each device type in the world list (validate_scene)
     unsigned char* scratch = nullptr;  // work space of the device build, reused across uploads
     size_t scratch_cap = 0;
 };
@@ -770,8 +772,42 @@ static int validate_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
         if (xf < -1 || xf >= sc->n_xforms) return "xform index out of range";
         return nullptr;
     };
-    for (int i = 0; i < sc->n_world; i++)
-        if (const char* m = check_ref(sc->world[i], false)) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: world[%d]: %s", i, m);
+    // the world list is the one O(n) part of validation: big scenes split it over the host cores,
+    // and count the primitives of each DEVICE type on the way (the device upload path sizes its
+    // arena blocks from these counts)
+    {
+        const int n = sc->n_world;
+        const int workers = n < (1 << 16) ? 1 : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        struct Part { int bad = -1; const char* msg = nullptr; size_t count[4] = {0, 0, 0, 0}; };
+        std::vector<Part> parts((size_t)workers);
+        auto run = [&](int w) {
+            Part& p = parts[(size_t)w];
+            const int a = (int)((long long)n * w / workers), b = (int)((long long)n * (w + 1) / workers);
+            for (int i = a; i < b; i++) {
+                const rt_prim_ref r = sc->world[i];
+                if (const char* m = check_ref(r, false)) { p.bad = i; p.msg = m; return; }
+                uint32_t t = r.type == RT_PRIM_QUAD ? PT_QUAD : (r.type == RT_PRIM_TRIANGLE ? PT_TRI : PT_SPHERE);
+                if (r.type == RT_PRIM_SPHERE) {
+                    const double* v = sc->spheres[r.index].center_vec;
+                    if (v[0] != 0 || v[1] != 0 || v[2] != 0) t = PT_MSPHERE;
+                }
+                p.count[t]++;
+            }
+        };
+        if (workers == 1) {
+            run(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (int w = 1; w < workers; w++) pool.emplace_back(run, w);
+            run(0);
+            for (auto& t : pool) t.join();
+        }
+        for (int k = 0; k < 4; k++) ctx->world_type_count[k] = 0;
+        for (const Part& p : parts) {
+            if (p.bad >= 0) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: world[%d]: %s", p.bad, p.msg);
+            for (int k = 0; k < 4; k++) ctx->world_type_count[k] += p.count[k];
+        }
+    }
     for (int i = 0; i < sc->n_boundary_refs; i++)
         if (const char* m = check_ref(sc->boundary_refs[i], true)) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: boundary_refs[%d]: %s", i, m);
     for (int i = 0; i < sc->n_media; i++) {
@@ -846,15 +882,7 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
     std::vector<BakedPrim> baked;
     rtbvh::Result bvh;
     if (device_build) {
-        for (int i = 0; i < sc->n_world; i++) {
-            const rt_prim_ref r = sc->world[i];
-            uint32_t t = r.type == RT_PRIM_QUAD ? PT_QUAD : (r.type == RT_PRIM_TRIANGLE ? PT_TRI : PT_SPHERE);
-            if (r.type == RT_PRIM_SPHERE) {
-                const double* v = sc->spheres[r.index].center_vec;
-                if (v[0] != 0 || v[1] != 0 || v[2] != 0) t = PT_MSPHERE;
-            }
-            world_count[t]++;
-        }
+        for (int k = 0; k < 4; k++) world_count[k] = ctx->world_type_count[k];
         baked.reserve((size_t)sc->n_boundary_refs);
         for (int i = 0; i < sc->n_boundary_refs; i++) baked.push_back(rtprep::bake_prim(src, sc->boundary_refs[i], -1));
     } else {
