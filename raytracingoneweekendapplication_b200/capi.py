@@ -220,6 +220,8 @@ def load_scenes() -> C.CDLL:
                                         C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     s.rtsc_write_exr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
     s.rtsc_write_pfm.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+    s.rtsc_load_obj.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_double)]
+    s.rtsc_load_obj.restype = C.c_void_p
     s.rtsc_scene_hash.argtypes = [C.c_void_p]
     s.rtsc_scene_hash.restype = C.c_uint64
     _scenes = s
@@ -257,6 +259,27 @@ class Scene:
             self.close()
         except Exception:
             pass
+
+
+class ObjScene(Scene):
+    """An OBJ file loaded by the host mirror's mesh::loadObj (fast path or the reference's structure)."""
+
+    def __init__(self, path: str, per_triangle: bool = False, with_media: bool = False, scale: float = 1.0):
+        self.name = path
+        self._s = load_scenes()
+        ms = (C.c_double * 2)()
+        self._h = self._s.rtsc_load_obj(path.encode(), int(per_triangle), int(with_media), scale, ms)
+        if not self._h:
+            raise ValueError(f"cannot load {path!r}")
+        self.load_ms, self.flatten_ms = ms[0], ms[1]
+        self.desc_ptr = self._s.rtsc_desc(self._h)
+        w, h, spp, depth = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._s.rtsc_frame(self._h, C.byref(w), C.byref(h), C.byref(spp), C.byref(depth))
+        self.width, self.height, self.spp, self.depth = w.value, h.value, spp.value, depth.value
+
+    @property
+    def hash(self) -> int:
+        return self._s.rtsc_scene_hash(self._h)
 
 
 def scene_names() -> list:

@@ -18,6 +18,7 @@
 #define RTB200_RTOW_HOST_H
 
 #include <algorithm>
+#include <charconv>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -30,7 +31,13 @@
 #include <memory>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "frame_io.h"
 #include "host_rng.h"
@@ -254,6 +261,59 @@ class hittable;
 
 namespace rtb200 {
 
+// std::vector whose resize() leaves trivially-constructible elements uninitialised: the big
+// record arrays (a million triangles = 104 MB) are then first touched by the threads that fill them.
+template <class T>
+struct default_init_allocator : std::allocator<T> {
+    template <class U> struct rebind { using other = default_init_allocator<U>; };
+    using std::allocator<T>::allocator;
+    template <class U> void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void*>(p)) U; }
+    template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+template <class T> using pod_vector = std::vector<T, default_init_allocator<T>>;
+
+// runs fn(part, n_parts) on up to 16 host threads (one part per thread; part 0 on the caller)
+template <class F>
+inline void parallel_parts(size_t n_parts, F&& fn) {
+    std::vector<std::thread> pool;
+    for (size_t i = 1; i < n_parts; i++) pool.emplace_back([&fn, i, n_parts] { fn(i, n_parts); });
+    fn((size_t)0, n_parts);
+    for (auto& t : pool) t.join();
+}
+// a whole file, read-only: mapped, not copied
+class mapped_file {
+  public:
+    explicit mapped_file(const char* path) {
+        fd = ::open(path, O_RDONLY);
+        if (fd < 0) return;
+        struct stat st;
+        if (::fstat(fd, &st) != 0) { ::close(fd); fd = -1; return; }
+        len = (size_t)st.st_size;
+        if (len == 0) return;
+        void* m = ::mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { ::close(fd); fd = -1; len = 0; return; }
+        ptr = (const char*)m;
+    }
+    ~mapped_file() {
+        if (ptr) ::munmap((void*)ptr, len);
+        if (fd >= 0) ::close(fd);
+    }
+    mapped_file(const mapped_file&) = delete;
+    mapped_file& operator=(const mapped_file&) = delete;
+    bool ok() const { return fd >= 0; }
+    const char* data() const { return ptr ? ptr : ""; }
+    size_t size() const { return len; }
+  private:
+    int fd = -1;
+    const char* ptr = nullptr;
+    size_t len = 0;
+};
+
+inline size_t host_parts(size_t work_items, size_t min_per_part) {
+    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+    return std::max<size_t>(1, std::min<size_t>({hw, (size_t)16, work_items / std::max<size_t>(1, min_per_part)}));
+}
+
 struct xform3 {
     double r[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     double t[3] = {0, 0, 0};
@@ -261,10 +321,10 @@ struct xform3 {
 
 // Owns the POD arrays of one flattened scene and hands out an rt_scene_desc view.
 struct flat_scene {
-    std::vector<rt_prim_ref> world, boundary_refs;
+    pod_vector<rt_prim_ref> world, boundary_refs;
     std::vector<rt_sphere> spheres;
     std::vector<rt_quad> quads;
-    std::vector<rt_triangle> triangles;
+    pod_vector<rt_triangle> triangles;
     std::vector<rt_medium> media;
     std::vector<rt_xform> xforms;
     std::vector<rt_material> materials;
@@ -382,6 +442,30 @@ class flattener {
         t.xform = current_xform();
         fs.triangles.push_back(t);
         add_ref(RT_PRIM_TRIANGLE, (int)fs.triangles.size() - 1);
+    }
+
+    // Bulk version for triangle_soup: `tris` already holds ABI records (positions, uvs); only the
+    // material and transform indices are resolved here.  One material lookup, one append.
+    void add_triangles(const pod_vector<rt_triangle>& tris, const shared_ptr<material>& m) {
+        if (tris.empty()) return;
+        const int mat = boundary_depth > 0 ? -1 : material_id(m);
+        const int xf = current_xform();
+        const size_t first = fs.triangles.size(), n = tris.size();
+        fs.triangles.resize(first + n);
+        pod_vector<rt_prim_ref>& refs = boundary_depth > 0 ? fs.boundary_refs : fs.world;
+        const size_t r0 = refs.size();
+        refs.resize(r0 + n);
+        rt_triangle* dst = fs.triangles.data() + first;
+        rt_prim_ref* ref = refs.data() + r0;
+        parallel_parts(host_parts(n, 1 << 15), [&](size_t part, size_t parts) {
+            const size_t a = n * part / parts, b = n * (part + 1) / parts;
+            std::memcpy(dst + a, tris.data() + a, (b - a) * sizeof(rt_triangle));
+            for (size_t i = a; i < b; i++) {
+                dst[i].material = mat;
+                dst[i].xform = xf;
+                ref[i] = rt_prim_ref{RT_PRIM_TRIANGLE, (int32_t)(first + i)};
+            }
+        });
     }
 
     // --- participating media (constant_medium.h:8-61) -------------------------------
@@ -763,6 +847,12 @@ class hittable {
     virtual ~hittable() = default;
     virtual aabb bounding_box() const = 0;
     virtual void flatten(rtb200::flattener& f) const = 0;
+    // For bvh_node's replay of the reference's median split, which only matters to
+    // constant_medium objects: does this subtree hold one, and how many objects of the
+    // reference's list does this object stand for (triangle_soup: one per triangle)?
+    virtual bool has_medium() const { return false; }
+    virtual size_t list_items() const { return 1; }
+    virtual aabb list_item_box(size_t) const { return bounding_box(); }
 };
 
 class hittable_list : public hittable {
@@ -778,6 +868,11 @@ class hittable_list : public hittable {
     aabb bounding_box() const override { return bbox; }
     void flatten(rtb200::flattener& f) const override {
         for (const auto& o : objects) o->flatten(f);
+    }
+    bool has_medium() const override {
+        for (const auto& o : objects)
+            if (o->has_medium()) return true;
+        return false;
     }
   private:
     aabb bbox;
@@ -875,6 +970,62 @@ inline std::shared_ptr<hittable_list> triangle_quad(const point3& orig, double h
     return sides;
 }
 
+// Many triangles of one material as ONE scene object.  The reference's
+// mesh.h:95-121 creates one shared_ptr<triangle> per face; a million-face OBJ then spends its load
+// time in the allocator.  A soup stores the faces in the layout the C ABI wants and flattens with
+// one append; it contributes its triangles to the canonical primitive numbering in order,
+// exactly as that many separate `triangle` objects would.
+class triangle_soup : public hittable {
+  public:
+    explicit triangle_soup(std::shared_ptr<material> m) : mat(m) {}
+    void reserve(size_t n) { tris.reserve(n); }
+    size_t size() const { return tris.size(); }
+    // same arguments as the seven-argument triangle constructor (triangle.h:30-44)
+    void add(const vec3& a, const vec3& b, const vec3& c, glm::vec2 t0, glm::vec2 t1, glm::vec2 t2) {
+        rt_triangle t;
+        std::memset(&t, 0, sizeof t);
+        for (int k = 0; k < 3; k++) { t.p0[k] = a[k]; t.p1[k] = b[k]; t.p2[k] = c[k]; }
+        t.uv0[0] = t0.x; t.uv0[1] = t0.y; t.uv1[0] = t1.x; t.uv1[1] = t1.y; t.uv2[0] = t2.x; t.uv2[1] = t2.y;
+        t.material = -1;
+        t.xform = -1;
+        tris.push_back(t);
+        for (int k = 0; k < 3; k++) {
+            lo[k] = std::min({lo[k], a[k], b[k], c[k]});
+            hi[k] = std::max({hi[k], a[k], b[k], c[k]});
+        }
+    }
+    // bulk interface for loaders that fill the records from several threads
+    static void fill(rt_triangle& t, const vec3& a, const vec3& b, const vec3& c, glm::vec2 t0, glm::vec2 t1, glm::vec2 t2) {
+        std::memset(&t, 0, sizeof t);
+        for (int k = 0; k < 3; k++) { t.p0[k] = a[k]; t.p1[k] = b[k]; t.p2[k] = c[k]; }
+        t.uv0[0] = t0.x; t.uv0[1] = t0.y; t.uv1[0] = t1.x; t.uv1[1] = t1.y; t.uv2[0] = t2.x; t.uv2[1] = t2.y;
+        t.material = -1;
+        t.xform = -1;
+    }
+    rt_triangle* grow(size_t n) {
+        tris.resize(tris.size() + n);
+        return tris.data() + tris.size() - n;
+    }
+    void merge_bounds(const double l[3], const double h[3]) {
+        for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], l[k]); hi[k] = std::max(hi[k], h[k]); }
+    }
+    aabb bounding_box() const override {
+        if (tris.empty()) return aabb();
+        return aabb(vec3(lo[0], lo[1], lo[2]), vec3(hi[0], hi[1], hi[2]));
+    }
+    void flatten(rtb200::flattener& f) const override { f.add_triangles(tris, mat); }
+    size_t list_items() const override { return tris.size(); }
+    aabb list_item_box(size_t k) const override {  // what triangle::set_bbox gives the k-th face
+        const rt_triangle& t = tris[k];
+        return aabb(vec3(std::min({t.p0[0], t.p1[0], t.p2[0]}), std::min({t.p0[1], t.p1[1], t.p2[1]}), std::min({t.p0[2], t.p1[2], t.p2[2]})),
+                    vec3(std::max({t.p0[0], t.p1[0], t.p2[0]}), std::max({t.p0[1], t.p1[1], t.p2[1]}), std::max({t.p0[2], t.p1[2], t.p2[2]})));
+    }
+  private:
+    std::shared_ptr<material> mat;
+    rtb200::pod_vector<rt_triangle> tris;
+    double lo[3] = {infinity, infinity, infinity}, hi[3] = {-infinity, -infinity, -infinity};
+};
+
 class translate : public hittable {
   public:
     translate(shared_ptr<hittable> obj, const vec3& off) : object(obj), offset(off) { bbox = object->bounding_box() + offset; }
@@ -884,6 +1035,7 @@ class translate : public hittable {
         object->flatten(f);
         f.pop();
     }
+    bool has_medium() const override { return object->has_medium(); }
   private:
     shared_ptr<hittable> object;
     vec3 offset;
@@ -918,6 +1070,7 @@ class rotate_y : public hittable {
         object->flatten(f);
         f.pop();
     }
+    bool has_medium() const override { return object->has_medium(); }
   private:
     shared_ptr<hittable> object;
     double sin_theta, cos_theta;
@@ -932,14 +1085,32 @@ class rotate_y : public hittable {
 // find those objects and records a multiplicity per child.
 class bvh_node : public hittable {
   public:
+    // bvh.h:13-45.  The tree itself is rebuilt by rt_upload_scene; what survives of the
+    // reference's median split is which list entries end up ALONE in a leaf, because such a leaf
+    // stores its object as both children (bvh.h:31-33) and a constant_medium hit twice per visit
+    // behaves like a medium of twice the density.  The split is replayed only when the
+    // list holds a medium at all; an object that stands for many list entries (triangle_soup)
+    // takes part with one box per entry, exactly as that many `triangle` objects would.
     bvh_node(hittable_list list) {
-        items.reserve(list.objects.size());
-        for (size_t i = 0; i < list.objects.size(); i++) items.push_back({list.objects[i], (int)i});
-        mult.assign(items.size(), 1);
-        bbox = aabb::empty();
-        for (const auto& it : items) bbox = aabb(bbox, it.obj->bounding_box());
         originals = list.objects;
+        mult.assign(originals.size(), 1);
+        bbox = aabb::empty();
+        bool sensitive = false;
+        for (const auto& o : originals) {
+            bbox = aabb(bbox, o->bounding_box());
+            sensitive = sensitive || o->has_medium();
+        }
+        if (!sensitive || originals.empty()) return;
+        size_t n = 0;
+        for (const auto& o : originals) n += o->list_items();
+        items.reserve(n);
+        for (size_t i = 0; i < originals.size(); i++) {
+            const size_t k = originals[i]->list_items();
+            if (k == 1) items.push_back({originals[i]->list_item_box(0), (int)i});
+            else for (size_t j = 0; j < k; j++) items.push_back({originals[i]->list_item_box(j), -1});
+        }
         if (!items.empty()) replay(0, items.size());
+        std::vector<item>().swap(items);
     }
     aabb bounding_box() const override { return bbox; }
     void flatten(rtb200::flattener& f) const override {
@@ -950,9 +1121,14 @@ class bvh_node : public hittable {
             f.multiplicity = saved;
         }
     }
+    bool has_medium() const override {
+        for (const auto& o : originals)
+            if (o->has_medium()) return true;
+        return false;
+    }
     int multiplicity_of(size_t insertion_index) const { return mult[insertion_index]; }
   private:
-    struct item { shared_ptr<hittable> obj; int index; };
+    struct item { aabb box; int index; };  // index < 0: one of many entries of a bulk object
     std::vector<item> items;
     std::vector<shared_ptr<hittable>> originals;
     std::vector<int> mult;
@@ -960,13 +1136,16 @@ class bvh_node : public hittable {
 
     void replay(size_t start, size_t end) {
         aabb span_box = aabb::empty();
-        for (size_t i = start; i < end; i++) span_box = aabb(span_box, items[i].obj->bounding_box());
+        for (size_t i = start; i < end; i++) span_box = aabb(span_box, items[i].box);
         const int axis = span_box.longest_axis();
         const size_t span = end - start;
-        if (span == 1) { mult[items[start].index] *= 2; return; }
+        if (span == 1) {
+            if (items[start].index >= 0) mult[items[start].index] *= 2;
+            return;
+        }
         if (span == 2) return;
         std::sort(items.begin() + start, items.begin() + end, [axis](const item& a, const item& b) {
-            return a.obj->bounding_box().axis_interval(axis).min < b.obj->bounding_box().axis_interval(axis).min;
+            return a.box.axis_interval(axis).min < b.box.axis_interval(axis).min;
         });
         const size_t mid = start + span / 2;
         replay(start, mid);
@@ -982,6 +1161,7 @@ class constant_medium : public hittable {
         : boundary(b), density(d), phase_function(make_shared<isotropic>(albedo)) {}
     aabb bounding_box() const override { return boundary->bounding_box(); }
     void flatten(rtb200::flattener& f) const override { f.add_medium(*boundary, density, phase_function); }
+    bool has_medium() const override { return true; }
   private:
     shared_ptr<hittable> boundary;
     double density;
@@ -1018,7 +1198,26 @@ class mesh {
     // of the face's first three corners (mesh.h:78-81 passes the same uv index list and
     // addTriangle reads entries [0],[1],[2]).  Vertex positions go through
     // the float mat4 before being widened to double (mesh.h:105-117).
+    // Which loader loadObj uses.  false (default): the fast path -- the file is read in one piece,
+    // numbers are parsed with std::from_chars (correctly rounded, like operator>>), and the faces go
+    // into ONE triangle_soup object.  true: the reference's own structure (mesh.h:22-92) -- a
+    // stringstream per line and one shared_ptr<triangle> per face.  Both give the same flattened
+    // scene, byte for byte (tests/test_obj_fast_path.py).
+    static bool& per_triangle_objects() {
+        static bool flag = false;
+        return flag;
+    }
+
     bool loadObj(const std::string path, hittable_list& world, const shared_ptr<lambertian> mat, glm::mat4 transform) {
+        return per_triangle_objects() ? loadObjReference(path, world, mat, transform) : loadObjFast(path, world, mat, transform);
+    }
+
+    // mesh.h:22-92.  Understands `v`, `vt` and `f a/b/c ...` records; 3- and 4-vertex
+    // faces.  A 4-vertex face becomes (0,1,2) and (0,2,3) but BOTH halves take the UVs
+    // of the face's first three corners (mesh.h:78-81 passes the same uv index list and
+    // addTriangle reads entries [0],[1],[2]).  Vertex positions go through
+    // the float mat4 before being widened to double (mesh.h:105-117).
+    bool loadObjReference(const std::string path, hittable_list& world, const shared_ptr<lambertian> mat, glm::mat4 transform) {
         std::ifstream file(path);
         if (!file.is_open()) {
             std::cerr << "Failed to open file: " << path << std::endl;
@@ -1061,6 +1260,190 @@ class mesh {
                 }
             }
         }
+        return true;
+    }
+
+    // The same records from the same file, without the per-line streams and per-face objects:
+    // the file is cut at line ends into one piece per host thread; every piece is parsed into its
+    // own vertex / texcoord / face lists (OBJ indices are absolute, so the pieces are independent),
+    // the lists are joined in file order, and the triangles are then written in parallel.
+    struct obj_piece {
+        std::vector<glm::vec3> positions;
+        std::vector<glm::vec2> texcoords;
+        std::vector<int> face;  // per face: count (3 or 4), v0..v3, t0..t2
+        size_t triangles = 0, first_triangle = 0;
+        double lo[3] = {infinity, infinity, infinity}, hi[3] = {-infinity, -infinity, -infinity};
+    };
+
+    static void parse_obj_piece(const char* p, const char* end, obj_piece& out) {
+        auto is_space = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; };
+        // operator>>(float): skips blanks, parses the longest valid number, leaves 0 on failure
+        auto read_float = [&](const char*& q, const char* e, float& v) {
+            while (q < e && is_space(*q)) q++;
+            const char* s = q;
+            if (s < e && *s == '+') s++;  // from_chars does not accept a leading '+', streams do
+            float x = 0.0f;
+            auto r = std::from_chars(s, e, x);
+            if (r.ec != std::errc() && r.ec != std::errc::result_out_of_range) return false;
+            v = x;
+            q = r.ptr;
+            return true;
+        };
+        auto read_int = [&](const char*& q, const char* e, int& v) {
+            const char* s = q;
+            if (s < e && *s == '+') s++;
+            int x = 0;
+            auto r = std::from_chars(s, e, x);
+            if (r.ec != std::errc()) return false;
+            v = x;
+            q = r.ptr;
+            return true;
+        };
+        out.positions.reserve((size_t)(end - p) / 64);
+        out.texcoords.reserve((size_t)(end - p) / 64);
+        out.face.reserve((size_t)(end - p) / 8);
+        int vi[5], ti[5];
+        while (p < end) {
+            const char* eol = (const char*)std::memchr(p, '\n', (size_t)(end - p));
+            const char* e = eol ? eol : end;
+            const char* q = p;
+            while (q < e && is_space(*q)) q++;
+            const char* tag = q;
+            while (q < e && !is_space(*q)) q++;
+            const size_t tl = (size_t)(q - tag);
+            if (tl == 1 && tag[0] == 'v') {
+                glm::vec3 v;
+                if (read_float(q, e, v.x) && read_float(q, e, v.y)) read_float(q, e, v.z);
+                out.positions.push_back(v);
+            } else if (tl == 2 && tag[0] == 'v' && tag[1] == 't') {
+                glm::vec2 t;
+                if (read_float(q, e, t.x)) read_float(q, e, t.y);
+                out.texcoords.push_back(t);
+            } else if (tl == 1 && tag[0] == 'f') {
+                int n = 0;
+                while (true) {
+                    while (q < e && is_space(*q)) q++;
+                    if (q >= e) break;
+                    const char* ce = q;
+                    while (ce < e && !is_space(*ce)) ce++;
+                    // cs >> v >> slash >> vt >> slash >> vn: every step only runs if the one before worked
+                    int v = 0, vt = 0;
+                    const char* c = q;
+                    if (read_int(c, ce, v) && c < ce) {
+                        c++;  // the separator (any character, as `char slash` accepts)
+                        read_int(c, ce, vt);
+                    }
+                    if (n < 5) { vi[n] = v - 1; ti[n] = vt - 1; }
+                    n++;
+                    q = ce;
+                }
+                if (n == 3 || n == 4) {
+                    const int rec[8] = {n, vi[0], vi[1], vi[2], n == 4 ? vi[3] : -1, ti[0], ti[1], ti[2]};
+                    out.face.insert(out.face.end(), rec, rec + 8);
+                } else if (n > 4) {
+                    std::cerr << "Skipping face with " << n << " vertices." << std::endl;
+                }
+            }
+            p = eol ? eol + 1 : end;
+        }
+    }
+
+    bool loadObjFast(const std::string& path, hittable_list& world, const shared_ptr<lambertian>& mat, const glm::mat4& transform) {
+        rtb200::mapped_file file(path.c_str());
+        if (!file.ok()) {
+            std::cerr << "Failed to open file: " << path << std::endl;
+            return false;
+        }
+        const char* const text = file.data();
+        const size_t got = file.size();
+
+        // ---- phase 1: parse, one piece per thread ------------------------------------------------
+        const size_t n_pieces = rtb200::host_parts(got, 1u << 20);
+        std::vector<size_t> cut(n_pieces + 1, got);
+        cut[0] = 0;
+        for (size_t i = 1; i < n_pieces; i++) {
+            size_t at = std::max(cut[i - 1], got * i / n_pieces);
+            const void* nl = at < got ? std::memchr(text + at, '\n', got - at) : nullptr;
+            cut[i] = nl ? (size_t)((const char*)nl - text) + 1 : got;
+        }
+        std::vector<obj_piece> pieces(n_pieces);
+        auto for_pieces = [&](auto&& fn) { rtb200::parallel_parts(n_pieces, [&fn](size_t i, size_t) { fn(i); }); };
+        for_pieces([&](size_t i) { parse_obj_piece(text + cut[i], text + cut[i + 1], pieces[i]); });
+
+        // ---- join the vertex lists in file order -----------------------------------------------------
+        std::vector<glm::vec3> positions;
+        std::vector<glm::vec2> texcoords;
+        {
+            size_t np = 0, nt = 0;
+            for (const obj_piece& pc : pieces) { np += pc.positions.size(); nt += pc.texcoords.size(); }
+            positions.reserve(np);
+            texcoords.reserve(nt);
+            for (obj_piece& pc : pieces) {
+                positions.insert(positions.end(), pc.positions.begin(), pc.positions.end());
+                texcoords.insert(texcoords.end(), pc.texcoords.begin(), pc.texcoords.end());
+                std::vector<glm::vec3>().swap(pc.positions);
+                std::vector<glm::vec2>().swap(pc.texcoords);
+            }
+        }
+        // ---- phase 2: count the triangles of every piece, then write them in parallel -------------------
+        const int nv = (int)positions.size();
+        auto face_ok = [&](const int* r, int a, int b, int c) {
+            const int v0 = r[1 + a], v1 = r[1 + b], v2 = r[1 + c];
+            return v0 >= 0 && v1 >= 0 && v2 >= 0 && v0 < nv && v1 < nv && v2 < nv;
+        };
+        for_pieces([&](size_t i) {
+            obj_piece& pc = pieces[i];
+            for (size_t k = 0; k + 8 <= pc.face.size(); k += 8) {
+                const int* r = &pc.face[k];
+                pc.triangles += face_ok(r, 0, 1, 2) ? 1 : 0;
+                if (r[0] == 4) pc.triangles += face_ok(r, 0, 2, 3) ? 1 : 0;
+            }
+        });
+        size_t total = 0, listed = 0;
+        for (obj_piece& pc : pieces) {
+            pc.first_triangle = total;
+            total += pc.triangles;
+            for (size_t k = 0; k + 8 <= pc.face.size(); k += 8) listed += pc.face[k] == 4 ? 2 : 1;
+        }
+        // the reference indexes vertices[] unchecked (undefined behaviour); such faces are refused here
+        if (listed != total) std::cerr << "Skipping " << (listed - total) << " triangles with a vertex index outside the file." << std::endl;
+        if (total == 0) return true;
+        auto soup = make_shared<triangle_soup>(mat);
+        rt_triangle* out = soup->grow(total);
+        const size_t m0 = mesh_matrices.size();
+        mesh_matrices.resize(m0 + total);
+        for_pieces([&](size_t i) {
+            obj_piece& pc = pieces[i];
+            size_t w = pc.first_triangle;
+            auto emit = [&](const int* r, int a, int b, int c) {
+                if (!face_ok(r, a, b, c)) return;
+                // mesh.h:105-117: float mat4 times float position, widened to double afterwards
+                glm::vec4 A = transform * glm::vec4(positions[r[1 + a]], 1.0f);
+                glm::vec4 B = transform * glm::vec4(positions[r[1 + b]], 1.0f);
+                glm::vec4 C = transform * glm::vec4(positions[r[1 + c]], 1.0f);
+                glm::mat4 m(1.0f);
+                m[0] = A; m[1] = B; m[2] = C; m[3] = glm::vec4(0, 0, 0, 1);
+                mesh_matrices[m0 + w] = m;
+                auto uv_at = [&](int k) {  // always the face's FIRST three texcoord indices
+                    int idx = r[5 + k];
+                    return (idx >= 0 && idx < (int)texcoords.size()) ? texcoords[idx] : glm::vec2(0, 0);
+                };
+                const vec3 a3(A.x, A.y, A.z), b3(B.x, B.y, B.z), c3(C.x, C.y, C.z);
+                triangle_soup::fill(out[w], a3, b3, c3, uv_at(0), uv_at(1), uv_at(2));
+                for (int k = 0; k < 3; k++) {
+                    pc.lo[k] = std::min({pc.lo[k], a3[k], b3[k], c3[k]});
+                    pc.hi[k] = std::max({pc.hi[k], a3[k], b3[k], c3[k]});
+                }
+                w++;
+            };
+            for (size_t k = 0; k + 8 <= pc.face.size(); k += 8) {
+                const int* r = &pc.face[k];
+                emit(r, 0, 1, 2);
+                if (r[0] == 4) emit(r, 0, 2, 3);
+            }
+        });
+        for (const obj_piece& pc : pieces) soup->merge_bounds(pc.lo, pc.hi);
+        world.add(soup);
         return true;
     }
 

@@ -6,6 +6,8 @@
 
 #include "scenes.h"
 
+#include <chrono>
+
 struct rtsc_scene {
     rtb200::flat_scene fs;
     rt_scene_desc desc;
@@ -94,6 +96,52 @@ int rtsc_render_resumable(const char* name, unsigned seed, const char* asset_dir
     if (spp_done) *spp_done = cam.last_spp_done;
     if (spp_resumed) *spp_resumed = cam.last_spp_resumed;
     return 0;
+}
+
+// mesh::loadObj on its own.  per_triangle = 1 selects the reference's structure
+// (one shared_ptr<triangle> per face, mesh.h:22-121), 0 the fast path (parallel parse, one
+// triangle_soup).  with_media adds three constant_medium spheres next to the mesh and wraps the list
+// in a bvh_node, which makes the flattened media multiplicities depend on the replayed median split
+// (Q15).  `ms` receives {load, bvh_node + flatten} in milliseconds.
+rtsc_scene* rtsc_load_obj(const char* path, int per_triangle, int with_media, float scale, double* ms) {
+    using clk = std::chrono::steady_clock;
+    rtsc_scene* s = new rtsc_scene();
+    hittable_list world;
+    auto mat = make_shared<lambertian>(color(0.5, 0.4, 0.3));
+    mesh m;
+    const bool saved = mesh::per_triangle_objects();
+    mesh::per_triangle_objects() = per_triangle != 0;
+    auto t0 = clk::now();
+    glm::mat4 xf = glm::scale(glm::translate(glm::mat4(1.0f), glm::vec3(0.25f, -0.5f, 1.0f)), glm::vec3(scale));
+    bool ok = m.loadObj(path, world, mat, xf);
+    auto t1 = clk::now();
+    mesh::per_triangle_objects() = saved;
+    if (!ok) { delete s; return nullptr; }
+    std::vector<point_light> lights;
+    if (with_media) {
+        world.add(make_shared<constant_medium>(make_shared<sphere>(point3(0, 0, 0), 0.3, mat), 0.5, color(1, 1, 1)));
+        world.add(make_shared<constant_medium>(make_shared<sphere>(point3(40, 3, -20), 2.0, mat), 0.2, color(0, 0, 0)));
+        world.add(make_shared<constant_medium>(make_shared<sphere>(point3(-1000, 0, 0), 5.0, mat), 0.1, color(0.2, 0.2, 0.2)));
+        hittable_list wrapped(make_shared<bvh_node>(world));
+        rtb200::flatten_scene(wrapped, lights, s->fs);
+    } else {
+        rtb200::flatten_scene(world, lights, s->fs);
+    }
+    auto t2 = clk::now();
+    if (ms) {
+        ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        ms[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    }
+    camera cam;
+    cam.lookfrom = point3(0, 2, 6);
+    cam.lookat = point3(0, 0, 0);
+    cam.background = color(0.7, 0.8, 1.0);
+    cam.vfov = 40;
+    cam.export_camera(s->fs.camera);
+    s->desc = s->fs.desc();
+    s->cfg.width = 320; s->cfg.height = 240; s->cfg.spp = 4; s->cfg.depth = 10;
+    s->max_depth = 10;
+    return s;
 }
 
 // The writers on their own (CPU tests): frame of w*h*3 floats -> file.

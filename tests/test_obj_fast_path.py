@@ -1,0 +1,133 @@
+"""mesh::loadObj fast path: the parallel parser + triangle_soup must hand
+rt_upload_scene exactly the bytes the reference-structured loader (mesh.h:22-121: a stringstream
+per line, one shared_ptr<triangle> per face) produces — same triangles, same order, same UV
+quirk (Q5), same media multiplicities (Q15) when a bvh_node wraps the list."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from raytracingoneweekendapplication_b200 import capi
+
+TRICKY = """# comment line
+v 0 0 0
+v 1.5 0 0
+v 1 1 0
+   v 0 1 0
+v -1e-1 2.5E+0 +0.75
+v 3 -2
+vt 0 0
+vt 1 0
+vt 1 1
+vt 0.25 0.75
+vn 0 0 1
+o thing
+g grp
+usemtl whatever
+s off
+
+f 1/1/1 2/2/1 3/3/1
+f 1/1 2/2 3/3 4/4
+f 1//1 2//1 3//1
+f 1 3 4
+f 4/4/1 3/3/1 2/2/1 1/1/1
+f 1/1/1 2/2/1 3/3/1 4/4/1 5/1/1
+f 5/9/1 6/2/1 1/0/1
+f 1/1/1 2/2/1
+f 2/3 3/1 5/2"""
+
+
+def _desc_bytes(sc):
+    d = sc.desc
+    tri = C.string_at(d.triangles, d.n_triangles * C.sizeof(capi.rt_triangle)) if d.n_triangles else b""
+    refs = C.string_at(d.world, d.n_world * C.sizeof(capi.rt_prim_ref)) if d.n_world else b""
+    media = C.string_at(d.media, d.n_media * C.sizeof(capi.rt_medium)) if d.n_media else b""
+    return d.n_triangles, tri, refs, media
+
+
+@pytest.mark.parametrize("newline,tail", [("\n", "\n"), ("\r\n", "\r\n"), ("\n", "")])
+def test_tricky_obj_gives_identical_scenes(built, tmp_path, newline, tail):
+    path = str(tmp_path / "tricky.obj")
+    with open(path, "w", newline="") as f:
+        f.write(TRICKY.replace("\n", newline) + tail)
+    fast, ref = capi.ObjScene(path, per_triangle=False, scale=1.5), capi.ObjScene(path, per_triangle=True, scale=1.5)
+    nf, tf, rf, _ = _desc_bytes(fast)
+    nr, tr, rr, _ = _desc_bytes(ref)
+    assert nf == nr == 9    # 5 triangles + 2 quads (4 triangles); the 5-gon and the 2-gon are skipped
+    assert tf == tr and rf == rr
+    assert fast.hash == ref.hash
+    # Q5: both halves of a quad carry the UVs of the face's first three corners
+    t = np.frombuffer(tf, dtype=np.dtype([("p", "<f8", 9), ("uv", "<f4", 6), ("m", "<i4"), ("x", "<i4")]))
+    assert np.array_equal(t["uv"][1], t["uv"][2])
+
+
+def test_bundled_mesh_and_generated_terrain_match(built, tmp_path):
+    from raytracingoneweekendapplication_b200.assets import ensure_assets
+
+    monkey = os.path.join(ensure_assets(), "blob.obj")
+    fast, ref = capi.ObjScene(monkey), capi.ObjScene(monkey, per_triangle=True)
+    assert fast.desc.n_triangles == ref.desc.n_triangles > 900
+    assert fast.hash == ref.hash
+    # a file big enough to be cut into several pieces (> 1 MB per piece)
+    k = 260
+    xs = np.linspace(-5, 5, k)
+    path = str(tmp_path / "terrain.obj")
+    with open(path, "w") as f:
+        for i in range(k):
+            for j in range(k):
+                f.write(f"v {xs[i]:.6f} {np.sin(xs[i]) * np.cos(xs[j]):.6f} {xs[j]:.6f}\nvt {i / (k - 1):.5f} {j / (k - 1):.5f}\n")
+        for i in range(k - 1):
+            for j in range(k - 1):
+                a, b, c, d = i * k + j + 1, (i + 1) * k + j + 1, (i + 1) * k + j + 2, i * k + j + 2
+                f.write(f"f {a}/{a} {b}/{b} {c}/{c} {d}/{d}\n")
+    assert os.path.getsize(path) > 3 << 20
+    fast, ref = capi.ObjScene(path), capi.ObjScene(path, per_triangle=True)
+    assert fast.desc.n_triangles == ref.desc.n_triangles == 2 * (k - 1) ** 2
+    assert _desc_bytes(fast) == _desc_bytes(ref)
+    assert fast.load_ms < ref.load_ms
+
+
+def test_media_multiplicity_is_the_same_with_a_soup(built, tmp_path):
+    """Q15: which constant_medium ends up alone in a leaf of the reference's median-split BVH must
+    not depend on whether the mesh is one soup or a thousand triangle objects."""
+    from raytracingoneweekendapplication_b200.assets import ensure_assets
+
+    monkey = os.path.join(ensure_assets(), "blob.obj")
+    fast, ref = capi.ObjScene(monkey, with_media=True), capi.ObjScene(monkey, per_triangle=True, with_media=True)
+    assert fast.desc.n_media == ref.desc.n_media == 3
+    assert _desc_bytes(fast) == _desc_bytes(ref)
+    assert fast.hash == ref.hash
+    mult = [fast.desc.media[i].multiplicity for i in range(3)]
+    assert all(m in (1, 2) for m in mult)
+
+
+def test_faces_that_point_outside_the_file_are_refused(built, tmp_path, capfd):
+    path = str(tmp_path / "bad.obj")
+    open(path, "w").write("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\nf 1 2 9\nf 0 1 2\n")
+    sc = capi.ObjScene(path)
+    assert sc.desc.n_triangles == 1
+    assert "outside the file" in capfd.readouterr().err
+
+
+def test_missing_file(built, tmp_path):
+    with pytest.raises(ValueError):
+        capi.ObjScene(str(tmp_path / "nope.obj"))
+
+
+@pytest.mark.gpu
+def test_fast_path_renders_the_same_image(built, tmp_path):
+    from raytracingoneweekendapplication_b200.assets import ensure_assets
+
+    monkey = os.path.join(ensure_assets(), "blob.obj")
+    frames = []
+    for per_triangle in (False, True):
+        sc = capi.ObjScene(monkey, per_triangle=per_triangle, with_media=True)
+        c = capi.Context(0)
+        c.upload(sc)
+        c.render(160, 120, 4, max_depth=10, seed=5)
+        frames.append(c.accum_download())
+        c.close()
+    assert np.array_equal(frames[0], frames[1])
+    assert frames[0][..., :3].sum() > 0
