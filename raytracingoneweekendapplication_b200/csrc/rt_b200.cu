@@ -434,6 +434,8 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __g
     }
 }
 
+#include "rt_kernel_v3.cuh"
+
 __global__ void aov_kernel(const __grid_constant__ DevScene S, int width, int height, int* __restrict__ prim_id,
                            float* __restrict__ t_out, float* __restrict__ normal, float* __restrict__ point,
                            float* __restrict__ uv, unsigned long long* counters) {
@@ -682,7 +684,12 @@ extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
     cudaFuncSetAttribute(render_kernel_v2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     if (const char* bv = getenv("RT_B200_BVH")) ctx->bvh_builder = strcmp(bv, "host") == 0 ? 1 : (strcmp(bv, "device") == 0 ? 2 : 0);
-    if (const char* kv = getenv("RT_B200_KERNEL")) ctx->kernel_version = strcmp(kv, "v1") == 0 ? 1 : (strcmp(kv, "wf") == 0 ? 3 : 2);
+    if (const char* kv = getenv("RT_B200_KERNEL"))
+        ctx->kernel_version = strcmp(kv, "v1") == 0 ? 1 : (strcmp(kv, "wf") == 0 ? 3 : (strcmp(kv, "v3") == 0 ? 4 : 2));
+    // v3 parks one path context per lane in shared memory: 23.5 KB per block, three blocks per SM
+    cudaFuncSetAttribute(render_kernel_v3<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 40);
+    cudaFuncSetAttribute(render_kernel_v3<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 40);
+    cudaFuncSetAttribute(render_kernel_v3<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 40);
     cudaFuncSetAttribute(rtwf::wf_extend<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(rtwf::wf_extend<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(rtwf::wf_shade<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -694,6 +701,10 @@ extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
         CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], render_kernel<false>, 256, 0));
         CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], render_kernel<true>, 256, 0));
         CU(ctx, cudaFuncGetAttributes(&fa, render_kernel<false>));
+    } else if (ctx->kernel_version == 4) {
+        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], render_kernel_v3<false, false>, 256, 0));
+        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], render_kernel_v3<true, false>, 256, 0));
+        CU(ctx, cudaFuncGetAttributes(&fa, render_kernel_v3<false, false>));
     } else {
         CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], render_kernel_v2<false, false>, 256, 0));
         CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], render_kernel_v2<true, false>, 256, 0));
@@ -1390,6 +1401,11 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
         } else if (ctx->kernel_version == 1) {
             if (stats) render_kernel<true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
             else render_kernel<false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+        } else if (ctx->kernel_version == 4) {
+            const bool lite = ctx->scene_lite && !getenv("RT_B200_NO_LITE");
+            if (stats) render_kernel_v3<true, false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            else if (lite) render_kernel_v3<false, true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            else render_kernel_v3<false, false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
         } else {
             // LITE: no triangles, no point lights, no defocus blur in this scene (see hit_prim)
             const bool lite = ctx->scene_lite && !getenv("RT_B200_NO_LITE");

@@ -160,15 +160,16 @@ def test_full_4k_frame_properties(ctx, scene_of):
 
 
 def test_both_kernel_versions_render_the_same_bits(built, scene_of):
-    """render_kernel (v1, fixed ownership), render_kernel_v2 (warp streams) and the wavefront
-    pipeline (rt_wavefront.cuh) schedule the same samples completely differently; fixed-point
-    sums make the frames bit-identical."""
+    """render_kernel (v1, fixed ownership), render_kernel_v2 (warp streams), render_kernel_v3 (two
+    path contexts per lane, rt_kernel_v3.cuh) and the wavefront pipeline (rt_wavefront.cuh)
+    schedule the same samples completely differently; fixed-point sums make the frames
+    bit-identical."""
     import os
 
     from raytracingoneweekendapplication_b200 import capi
 
     frames = []
-    for version in ("v1", "v2", "wf"):
+    for version in ("v1", "v2", "wf", "v3"):
         os.environ["RT_B200_KERNEL"] = version
         try:
             c = capi.Context(0)
@@ -180,6 +181,21 @@ def test_both_kernel_versions_render_the_same_bits(built, scene_of):
         c.close()
     assert np.array_equal(frames[0], frames[1])
     assert np.array_equal(frames[0], frames[2])   # the wavefront pipeline too
+    assert np.array_equal(frames[0], frames[3])   # and the two-context kernel
+    # v3 again on the scenes whose paths are longest (media, 50 bounces) and with the pool running dry
+    for name, w, h, spp in (("final", 200, 112, 5), ("cornell_smoke", 96, 96, 9), ("mesh", 160, 90, 3)):
+        pair = []
+        for version in ("v2", "v3"):
+            os.environ["RT_B200_KERNEL"] = version
+            try:
+                c = capi.Context(0)
+            finally:
+                os.environ.pop("RT_B200_KERNEL", None)
+            c.upload(scene_of(name))
+            c.render(w, h, spp, seed=2)
+            pair.append(c.accum_download())
+            c.close()
+        assert np.array_equal(pair[0], pair[1]), name
 
 
 def test_lite_kernel_instance_renders_the_same_bits(ctx, scene_of):
