@@ -28,6 +28,10 @@
 #pragma once
 #include <cub/cub.cuh>
 
+#include <algorithm>
+#include <cstring>
+#include <thread>
+
 #include "prim_derive.h"
 
 namespace rtlbvh {
@@ -334,6 +338,67 @@ inline Layout plan_scratch(const rt_scene_desc* sc) {
     return L;
 }
 
+// Host -> device copy of a big PAGEABLE array.  cudaMemcpyAsync from pageable memory is staged by
+// the driver on one thread (~10 GB/s measured on this box); here `kCopyWorkers` host threads copy
+// 4 MB chunks into pinned buffers (two per worker) and enqueue the DMA of each chunk themselves, so
+// that staging and PCIe transfer overlap and the staging itself runs on several cores.
+constexpr size_t kCopyChunk = 4u << 20;
+constexpr int kCopyWorkers = 4;
+constexpr size_t kCopyRingBytes = kCopyChunk * 2 * kCopyWorkers;
+
+struct CopyRing {
+    unsigned char* pinned = nullptr;  // kCopyRingBytes
+    cudaEvent_t done[2 * kCopyWorkers] = {};
+    bool ready = false;
+    cudaError_t init() {
+        if (ready) return cudaSuccess;
+        cudaError_t e = cudaHostAlloc((void**)&pinned, kCopyRingBytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        for (auto& ev : done)
+            if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        ready = true;
+        return cudaSuccess;
+    }
+    void release() {
+        if (pinned) cudaFreeHost(pinned);
+        pinned = nullptr;
+        if (ready) for (auto& ev : done) cudaEventDestroy(ev);
+        ready = false;
+    }
+};
+
+inline cudaError_t copy_in(void* dst, const void* src, size_t bytes, cudaStream_t stream, CopyRing& ring, int device) {
+    if (bytes == 0) return cudaSuccess;
+    if (bytes < 4 * kCopyChunk || !ring.ready) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+    const size_t n_chunks = (bytes + kCopyChunk - 1) / kCopyChunk;
+    cudaError_t err[kCopyWorkers];
+    auto work = [&](int w) {
+        err[w] = cudaSetDevice(device);
+        bool used[2] = {false, false};
+        for (size_t c = (size_t)w, k = 0; c < n_chunks && err[w] == cudaSuccess; c += kCopyWorkers, k++) {
+            const int slot = 2 * w + (int)(k & 1);
+            unsigned char* buf = ring.pinned + (size_t)slot * kCopyChunk;
+            if (used[k & 1]) err[w] = cudaEventSynchronize(ring.done[slot]);  // the DMA that last read this buffer
+            if (err[w] != cudaSuccess) break;
+            const size_t off = c * kCopyChunk, len = std::min(kCopyChunk, bytes - off);
+            std::memcpy(buf, (const unsigned char*)src + off, len);
+            err[w] = cudaMemcpyAsync((unsigned char*)dst + off, buf, len, cudaMemcpyHostToDevice, stream);
+            if (err[w] == cudaSuccess) err[w] = cudaEventRecord(ring.done[slot], stream);
+            used[k & 1] = true;
+        }
+        // the buffers must not be reused by the next copy_in before their DMA finished
+        for (int b = 0; b < 2 && err[w] == cudaSuccess; b++)
+            if (used[b]) err[w] = cudaEventSynchronize(ring.done[2 * w + b]);
+    };
+    std::thread pool[kCopyWorkers - 1];
+    for (int w = 1; w < kCopyWorkers; w++) pool[w - 1] = std::thread(work, w);
+    work(0);
+    for (auto& t : pool) t.join();
+    for (int w = 0; w < kCopyWorkers; w++)
+        if (err[w] != cudaSuccess) return err[w];
+    return cudaSuccess;
+}
+
 struct BuildResult {
     unsigned nodes = 0, leaves = 0, depth = 0;
     float ms_copy_in = 0, ms_build = 0, ms_emit = 0;
@@ -342,7 +407,7 @@ struct BuildResult {
 // Copies the raw arrays of `sc` into `scratch` and runs the build on `stream`.  `T` points into
 // the scene arena.  Returns a cudaError_t-compatible code (0 = success).
 inline cudaError_t build_on_device(const rt_scene_desc* sc, unsigned char* scratch, const Layout& L, const Targets& T,
-                                   cudaStream_t stream, BuildResult& out) {
+                                   cudaStream_t stream, CopyRing& ring, int device, BuildResult& out) {
     const int n = sc->n_world;
     Scratch W{};
     auto at = [&](size_t off) { return scratch + off; };
@@ -351,7 +416,7 @@ inline cudaError_t build_on_device(const rt_scene_desc* sc, unsigned char* scrat
     for (auto& v : ev) if ((e = cudaEventCreate(&v)) != cudaSuccess) return e;
     cudaEventRecord(ev[0], stream);
 #define RT_COPY_IN(field, ptr, count, type)                                                                                   \
-    if ((count) > 0 && (e = cudaMemcpyAsync(at(L.field), ptr, (size_t)(count) * sizeof(type), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+    if ((count) > 0 && (e = copy_in(at(L.field), ptr, (size_t)(count) * sizeof(type), stream, ring, device)) != cudaSuccess) return e;
     RT_COPY_IN(world, sc->world, n, rt_prim_ref)
     RT_COPY_IN(spheres, sc->spheres, sc->n_spheres, rt_sphere)
     RT_COPY_IN(quads, sc->quads, sc->n_quads, rt_quad)

@@ -598,6 +598,7 @@ struct rt_ctx {
     // scene-upload path: 0 auto (device LBVH from kDeviceBuildAuto primitives up), 1 host SAH, 2 device LBVH
     int bvh_builder = 0;
     size_t world_type_count[4] = {0, 0, 0, 0};  // primitives of each device type in the world list (validate_scene)
+    rtlbvh::CopyRing copy_ring;        // pinned staging of the device path's raw-input copy
     unsigned char* scratch = nullptr;  // work space of the device build, reused across uploads
     size_t scratch_cap = 0;
 };
@@ -630,6 +631,7 @@ static void free_scene(rt_ctx* ctx) { ctx->has_scene = false; }
 static void release_buffers(rt_ctx* ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->copy_ring.release();
     ctx->scratch = nullptr;
     ctx->scratch_cap = 0;
     if (ctx->pool_mem) cudaFree(ctx->pool_mem);
@@ -1109,7 +1111,10 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
         T.sph_d = (double*)S.sph_d; T.msph_d = (double*)S.msph_d; T.quad_d = (double*)S.quad_d; T.tri_d = (double*)S.tri_d;
         T.sph_sh = (int4*)S.sph_sh; T.msph_sh = (int4*)S.msph_sh; T.quad_sh = (int4*)S.quad_sh;
         rtlbvh::BuildResult br;
-        CU(ctx, rtlbvh::build_on_device(sc, ctx->scratch, L, T, ctx->stream, br));
+        if ((size_t)sc->n_triangles * sizeof(rt_triangle) >= 4 * rtlbvh::kCopyChunk || (size_t)sc->n_quads * sizeof(rt_quad) >= 4 * rtlbvh::kCopyChunk ||
+            (size_t)sc->n_spheres * sizeof(rt_sphere) >= 4 * rtlbvh::kCopyChunk)
+            CU(ctx, ctx->copy_ring.init());
+        CU(ctx, rtlbvh::build_on_device(sc, ctx->scratch, L, T, ctx->stream, ctx->copy_ring, ctx->device, br));
         n_nodes = br.nodes;
         depth = br.depth;
         leaves = br.leaves;
