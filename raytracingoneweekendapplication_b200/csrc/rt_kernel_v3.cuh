@@ -1,6 +1,6 @@
 // rt_kernel_v3.cuh — render_kernel_v3: the v2 megakernel with TWO path contexts per lane.
 //
-// Measured on v2 (profiles/r1_bench_n1_lane_occupancy.json): a BVH node step runs with 12 of 32
+// Measured on v2 (profiles/r1_bench_n1.json, key `lane_occupancy`): a BVH node step runs with 12 of 32
 // lanes working — 13 hold a leaf and wait for the others to arrive, 7 have finished their ray and
 // wait for the phase to end.  v3 gives every lane a second path: one context lives in registers
 // (as in v2), the other is PARKED in shared memory (23 words per lane, field-major so that a
