@@ -266,6 +266,7 @@ typedef struct rt_stats {
      * built by CUDA kernels, with the device time of the build and of the raw-input copy */
     uint32_t bvh_on_device, reserved_;
     double device_build_ms, device_copy_in_ms;
+    double device_top_ms; /* host time of the SAH top levels of the device-built tree (sync + copies included) */
 } rt_stats;
 
 /* Create a context on CUDA device `device_ids[0]` (n_devices must be 1: this
@@ -283,7 +284,9 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene);
 /* Which builder rt_upload_scene uses (replaces bvh.h:13-45 either way).
  *   1 host:   transforms baked, binned-SAH BVH2 and device records built on the CPU (best tree)
  *   2 device: raw arrays copied as they are; LBVH (Morton sort + radix tree) and device records
- *             built by CUDA kernels: ~100x faster upload for million-primitive scenes, slower tree
+ *             built by CUDA kernels, the top levels of the tree rebuilt with SAH on the host over a
+ *             few thousand clusters: ~100x faster upload for million-primitive scenes
+ *   3 device, without the SAH top levels (pure LBVH; for comparison)
  *   0 auto:   device from 2^20 primitives up (environment RT_B200_BVH=host|device overrides at rt_create)
  * Images do not depend on the choice (same records bit for bit, closest hit is tree-independent)
  * except where two primitives are hit at exactly the same t. */

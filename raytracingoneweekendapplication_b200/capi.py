@@ -120,6 +120,7 @@ class rt_stats(C.Structure):
         ("leaf_lanes", C.c_uint64), ("shade_iters", C.c_uint64), ("shade_lanes", C.c_uint64),
         ("trav_hist", C.c_uint64 * 208),
         ("bvh_on_device", C.c_uint32), ("reserved_", C.c_uint32), ("device_build_ms", C.c_double), ("device_copy_in_ms", C.c_double),
+        ("device_top_ms", C.c_double),
     ]
 
     def as_dict(self) -> dict:
@@ -308,8 +309,9 @@ class Context:
             raise RtError(rc, self.lib.rt_last_error(self._h).decode())
 
     def set_bvh_builder(self, mode: str) -> None:
-        """'auto' | 'host' (binned SAH on the CPU) | 'device' (LBVH in CUDA kernels) for the next upload."""
-        self._check(self.lib.rt_set_bvh_builder(self._h, {"auto": 0, "host": 1, "device": 2}[mode]))
+        """'auto' | 'host' (binned SAH on the CPU) | 'device' (LBVH in CUDA kernels + SAH top levels) |
+        'lbvh' (device, pure LBVH) for the next upload."""
+        self._check(self.lib.rt_set_bvh_builder(self._h, {"auto": 0, "host": 1, "device": 2, "lbvh": 3}[mode]))
 
     def upload(self, scene) -> None:
         if hasattr(scene, "desc_ptr"):          # capi.Scene or any object that keeps a description alive

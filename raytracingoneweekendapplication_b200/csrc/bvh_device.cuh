@@ -32,6 +32,11 @@
 #include <cstring>
 #include <thread>
 
+#include <chrono>
+#include <cstdlib>
+#include <vector>
+
+#include "bvh_build.h"
 #include "prim_derive.h"
 
 namespace rtlbvh {
@@ -39,7 +44,10 @@ namespace rtlbvh {
 using rtprep::BakedPrim;
 using rtprep::Sources;
 
-constexpr int kMaxLeaf = 4;
+#ifndef RT_LBVH_MAX_LEAF
+#define RT_LBVH_MAX_LEAF 4
+#endif
+constexpr int kMaxLeaf = RT_LBVH_MAX_LEAF;
 
 struct Targets {  // arena blocks the device path fills (world part of each typed array)
     float4* nodes;
@@ -56,6 +64,7 @@ struct Scratch {
     unsigned long long *key_in, *key_out;  // Morton codes
     uint32_t *val_in, *val_out;            // primitive index
     uint32_t *flag, *scan, *rank_at;       // per sorted position
+    float* cost;                           // per internal node: SAH cost (aliases `flag`, which is dead after the rank passes)
     int *left, *right, *parent_int, *parent_leaf, *range_first;
     float4 *nbox_lo, *nbox_hi;             // per internal node; lo.w = count bits, hi.w = type mask | height << 8
     unsigned* visit;
@@ -185,7 +194,19 @@ __global__ void __launch_bounds__(256) karras_kernel(Scratch W) {
 struct NodeInfo {
     float lo[3], hi[3];
     unsigned count, mask, height;
+    float cost;    // SAH cost of the best way to finish this subtree (leaf or split), times the root-independent 1/area factor left out
+    bool as_leaf;  // ... and whether that best way is ONE leaf
 };
+__device__ __forceinline__ float box_area(const float lo[3], const float hi[3]) {
+    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return 2.0f * (dx * dy + dy * dz + dz * dx);
+}
+// relative intersection cost of the primitive types, as the host builder's rtbvh::Prim::cost
+__device__ __forceinline__ float prim_cost(unsigned type) { return type == rtprep::PREP_SPHERE ? 1.0f : (type == rtprep::PREP_MSPHERE ? 1.2f : 1.3f); }
+#ifndef RT_LBVH_TRAV_COST
+#define RT_LBVH_TRAV_COST 3.0f
+#endif
+constexpr float kTravCost = RT_LBVH_TRAV_COST;  // one node visit, in sphere tests (rtbvh::Tuning::trav_cost)
 __device__ __forceinline__ NodeInfo child_info(const Scratch& W, int c) {
     NodeInfo r;
     if (c < 0) {
@@ -196,14 +217,18 @@ __device__ __forceinline__ NodeInfo child_info(const Scratch& W, int c) {
         r.count = 1u;
         r.mask = 1u << __float_as_uint(lo.w);
         r.height = 0u;
+        r.cost = box_area(r.lo, r.hi) * prim_cost(__float_as_uint(lo.w));
+        r.as_leaf = true;
     } else {
         // written by another thread of this launch: read through L2
         const float4 lo = __ldcg(W.nbox_lo + c), hi = __ldcg(W.nbox_hi + c);
         r.lo[0] = lo.x; r.lo[1] = lo.y; r.lo[2] = lo.z;
         r.hi[0] = hi.x; r.hi[1] = hi.y; r.hi[2] = hi.z;
         r.count = __float_as_uint(lo.w);
-        r.mask = __float_as_uint(hi.w) & 0xffu;
+        r.mask = __float_as_uint(hi.w) & 0x0fu;
+        r.as_leaf = (__float_as_uint(hi.w) & 0x80u) != 0u;
         r.height = __float_as_uint(hi.w) >> 8;
+        r.cost = __ldcg(W.cost + c);
     }
     return r;
 }
@@ -218,15 +243,27 @@ __global__ void __launch_bounds__(256) fit_kernel(Scratch W) {
         __threadfence();
         const NodeInfo a = child_info(W, W.left[p]), b = child_info(W, W.right[p]);
         const unsigned height = max(a.height, b.height) + 1u;
-        __stcg(W.nbox_lo + p, make_float4(fminf(a.lo[0], b.lo[0]), fminf(a.lo[1], b.lo[1]), fminf(a.lo[2], b.lo[2]), __uint_as_float(a.count + b.count)));
-        __stcg(W.nbox_hi + p, make_float4(fmaxf(a.hi[0], b.hi[0]), fmaxf(a.hi[1], b.hi[1]), fmaxf(a.hi[2], b.hi[2]),
-                                         __uint_as_float((a.mask | b.mask) | (height << 8))));
+        float lo[3], hi[3];
+        for (int k = 0; k < 3; k++) { lo[k] = fminf(a.lo[k], b.lo[k]); hi[k] = fmaxf(a.hi[k], b.hi[k]); }
+        const unsigned count = a.count + b.count, mask = a.mask | b.mask;
+        // surface-area heuristic, bottom-up: one leaf of `count` primitives of one type, or a node
+        // visit plus the best of the two subtrees
+        const float area = box_area(lo, hi);
+        const float split_cost = kTravCost * area + a.cost + b.cost;
+        const bool can_leaf = count <= (unsigned)kMaxLeaf && __popc(mask) == 1;
+        const float leaf_cost = area * (float)count * prim_cost(31u - __clz(mask));
+        const bool as_leaf = can_leaf && leaf_cost <= split_cost;
+        __stcg(W.cost + p, as_leaf ? leaf_cost : split_cost);
+        __stcg(W.nbox_lo + p, make_float4(lo[0], lo[1], lo[2], __uint_as_float(count)));
+        __stcg(W.nbox_hi + p, make_float4(hi[0], hi[1], hi[2], __uint_as_float(mask | (as_leaf ? 0x80u : 0u) | (height << 8))));
         if (p == 0) W.counters[2] = height;
         p = W.parent_int[p];
     }
 }
 
-__device__ __forceinline__ bool collapsible(const NodeInfo& v) { return v.count <= (unsigned)kMaxLeaf && __popc(v.mask) == 1; }
+// A subtree becomes ONE leaf where the SAH says so (and the leaf encoding allows it: <= kMaxLeaf
+// primitives of one type).  Nodes below such a subtree root are never referenced.
+__device__ __forceinline__ bool collapsible(const NodeInfo& v) { return v.as_leaf; }
 
 __global__ void __launch_bounds__(256) nodes_kernel(Scratch W, Targets T) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -259,6 +296,40 @@ __global__ void __launch_bounds__(256) nodes_kernel(Scratch W, Targets T) {
     dst[0] = out[0]; dst[1] = out[1]; dst[2] = out[2]; dst[3] = out[3];
     atomicAdd(&W.counters[0], 1u);
     if (leaves) atomicAdd(&W.counters[1], leaves);
+}
+
+// ---- hybrid top levels (HLBVH): the radix tree is cut where subtrees drop to <= max_count
+// primitives; the cut ("clusters": a few thousand boxes) goes to the host, which builds the TOP of
+// the tree over them with the same binned-SAH builder the host path uses, and comes back as a few
+// thousand 64-byte nodes whose leaves link into the radix tree.  The Morton order decides only
+// the small-scale structure; the large-scale structure, where LBVH trees lose most, is SAH.
+struct Cluster {
+    float lo[3];
+    int link;  // what a top-tree leaf points at: a radix-tree node (>= 0) or a leaf link (< 0)
+    float hi[3];
+    unsigned count;
+};
+
+__global__ void __launch_bounds__(256) clusters_kernel(Scratch W, unsigned max_count, Cluster* out, unsigned cap) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = W.n;
+    if (idx >= 2 * n - 1) return;
+    int parent, me;
+    if (idx < n - 1) { me = idx; parent = W.parent_int[idx]; }
+    else { me = ~(idx - (n - 1)); parent = W.parent_leaf[idx - (n - 1)]; }
+    const NodeInfo v = child_info(W, me);
+    if (v.count > max_count) return;
+    if (parent >= 0 && __float_as_uint(W.nbox_lo[parent].w) <= max_count) return;  // an ancestor is the cluster
+    const unsigned slot = atomicAdd(&W.counters[3], 1u);
+    atomicMax(&W.counters[2], v.height);  // re-used below as "tallest cluster" (the caller reads the root height first)
+    if (slot >= cap) return;
+    Cluster c;
+    for (int k = 0; k < 3; k++) { c.lo[k] = v.lo[k]; c.hi[k] = v.hi[k]; }
+    c.count = v.count;
+    if (me < 0) c.link = rtprep::leaf_link(31u - __clz(v.mask), 1u, W.rank_at[~me]);
+    else if (collapsible(v)) c.link = rtprep::leaf_link(31u - __clz(v.mask), v.count, W.rank_at[W.range_first[me]]);
+    else c.link = me;
+    out[slot] = c;
 }
 
 __device__ __forceinline__ float4 f4(rtprep::F4 v) { return make_float4(v.x, v.y, v.z, v.w); }
@@ -295,6 +366,8 @@ __global__ void __launch_bounds__(256) prims_kernel(Scratch W, Targets T) {
 }
 
 // ---- host side ---------------------------------------------------------------------------------
+constexpr unsigned kMaxClusters = 16384;  // capacity of the cut handed to the host (and of the top tree)
+
 struct ScratchPlan {
     size_t size = 0;
     size_t add(size_t bytes) {
@@ -307,7 +380,7 @@ struct ScratchPlan {
 struct Layout {
     size_t world, spheres, quads, triangles, xforms;
     size_t box_lo, box_hi, key_in, key_out, val_in, val_out, flag, scan, rank_at, left, right, parent_int, parent_leaf, range_first,
-        nbox_lo, nbox_hi, visit, bounds, counters, cub_temp;
+        nbox_lo, nbox_hi, visit, bounds, counters, cub_temp, clusters;
     size_t cub_temp_bytes, total;
 };
 
@@ -334,6 +407,7 @@ inline Layout plan_scratch(const rt_scene_desc* sc) {
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
     L.cub_temp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
     L.cub_temp = p.add(L.cub_temp_bytes);
+    L.clusters = p.add((size_t)kMaxClusters * sizeof(Cluster));
     L.total = p.size;
     return L;
 }
@@ -401,13 +475,15 @@ inline cudaError_t copy_in(void* dst, const void* src, size_t bytes, cudaStream_
 
 struct BuildResult {
     unsigned nodes = 0, leaves = 0, depth = 0;
-    float ms_copy_in = 0, ms_build = 0, ms_emit = 0;
+    int root = 0;            // index of the root node in the node array
+    unsigned top_nodes = 0;  // nodes of the SAH top tree appended after the n - 1 radix-tree slots (0: pure LBVH)
+    float ms_copy_in = 0, ms_build = 0, ms_emit = 0, ms_top = 0;
 };
 
 // Copies the raw arrays of `sc` into `scratch` and runs the build on `stream`.  `T` points into
 // the scene arena.  Returns a cudaError_t-compatible code (0 = success).
 inline cudaError_t build_on_device(const rt_scene_desc* sc, unsigned char* scratch, const Layout& L, const Targets& T,
-                                   cudaStream_t stream, CopyRing& ring, int device, BuildResult& out) {
+                                   cudaStream_t stream, CopyRing& ring, int device, bool hybrid_top, BuildResult& out) {
     const int n = sc->n_world;
     Scratch W{};
     auto at = [&](size_t off) { return scratch + off; };
@@ -432,6 +508,7 @@ inline cudaError_t build_on_device(const rt_scene_desc* sc, unsigned char* scrat
     W.key_in = (unsigned long long*)at(L.key_in); W.key_out = (unsigned long long*)at(L.key_out);
     W.val_in = (uint32_t*)at(L.val_in); W.val_out = (uint32_t*)at(L.val_out);
     W.flag = (uint32_t*)at(L.flag); W.scan = (uint32_t*)at(L.scan); W.rank_at = (uint32_t*)at(L.rank_at);
+    W.cost = (float*)at(L.flag);
     W.left = (int*)at(L.left); W.right = (int*)at(L.right); W.parent_int = (int*)at(L.parent_int);
     W.parent_leaf = (int*)at(L.parent_leaf); W.range_first = (int*)at(L.range_first);
     W.nbox_lo = (float4*)at(L.nbox_lo); W.nbox_hi = (float4*)at(L.nbox_hi);
@@ -464,6 +541,53 @@ inline cudaError_t build_on_device(const rt_scene_desc* sc, unsigned char* scrat
     out.nodes = c[0];
     out.leaves = c[1];
     out.depth = c[2];
+    out.root = 0;
+    out.top_nodes = 0;
+    // ---- SAH top levels over the cut of the radix tree ------------------------------------------
+    unsigned max_count = std::max<unsigned>(64u, (unsigned)(2ull * (unsigned long long)n / (kMaxClusters / 2)));
+    if (const char* ev_c = getenv("RT_B200_CLUSTER")) max_count = std::max(2, atoi(ev_c));  // tuning experiments
+    if (hybrid_top && (unsigned)n > 4 * max_count) {
+        auto t0 = std::chrono::steady_clock::now();
+        Cluster* d_clusters = (Cluster*)at(L.clusters);
+        const unsigned zero[2] = {0u, 0u};
+        if ((e = cudaMemcpyAsync(W.counters + 2, zero, sizeof zero, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        clusters_kernel<<<(2 * n - 1 + tpb - 1) / tpb, tpb, 0, stream>>>(W, max_count, d_clusters, kMaxClusters);
+        if ((e = cudaMemcpyAsync(c, W.counters, sizeof c, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+        const unsigned n_clusters = c[3], tallest = c[2];
+        if (n_clusters >= 2 && n_clusters <= kMaxClusters) {
+            std::vector<Cluster> cl(n_clusters);
+            if ((e = cudaMemcpy(cl.data(), d_clusters, n_clusters * sizeof(Cluster), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+            std::vector<rtbvh::Prim> items(n_clusters);
+            for (unsigned i = 0; i < n_clusters; i++) {
+                rtbvh::Prim& p = items[i];
+                for (int k = 0; k < 3; k++) { p.box.lo[k] = cl[i].lo[k]; p.box.hi[k] = cl[i].hi[k]; p.centroid[k] = 0.5f * (cl[i].lo[k] + cl[i].hi[k]); }
+                p.type = 0;
+                p.index = i;
+                p.cost = (float)cl[i].count;
+            }
+            rtbvh::Tuning tune;
+            tune.max_leaf = 1;
+            rtbvh::Result top;
+            rtbvh::build_bvh(items, top, tune, 1);
+            // leaves of the top tree are (type 0, count 1, first = position in top.order): point them at the clusters
+            const int base = n - 1;
+            auto relink = [&](int32_t link) -> int32_t {
+                if (link >= 0) return link + base;
+                const uint32_t first = (~(uint32_t)link) & 0x01ffffffu;
+                return cl[top.order[first]].link;
+            };
+            for (rtbvh::Node& nd : top.nodes) { nd.llink = relink(nd.llink); nd.rlink = relink(nd.rlink); }
+            if (top.root >= 0 && !top.nodes.empty()) {
+                if ((e = cudaMemcpy(T.nodes + 4 * (size_t)base, top.nodes.data(), top.nodes.size() * sizeof(rtbvh::Node), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+                out.root = top.root + base;
+                out.top_nodes = (unsigned)top.nodes.size();
+                out.depth = top.depth + tallest;
+                out.nodes += out.top_nodes;
+            }
+        }
+        out.ms_top = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
     cudaEventElapsedTime(&out.ms_copy_in, ev[0], ev[1]);
     cudaEventElapsedTime(&out.ms_build, ev[1], ev[2]);
     cudaEventElapsedTime(&out.ms_emit, ev[2], ev[3]);

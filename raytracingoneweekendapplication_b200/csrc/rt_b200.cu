@@ -595,7 +595,7 @@ struct rt_ctx {
     int wf_blocks_per_sm[2] = {0, 0};
     int blocks_per_sm[2] = {0, 0};
     bool pending_async = false;
-    // scene-upload path: 0 auto (device LBVH from kDeviceBuildAuto primitives up), 1 host SAH, 2 device LBVH
+    // scene-upload path: 0 auto (device from kDeviceBuildAuto primitives up), 1 host SAH, 2 device (LBVH + SAH top levels), 3 device, pure LBVH
     int bvh_builder = 0;
     size_t world_type_count[4] = {0, 0, 0, 0};  // primitives of each device type in the world list (validate_scene)
     rtlbvh::CopyRing copy_ring;        // pinned staging of the device path's raw-input copy
@@ -685,7 +685,8 @@ extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
     cudaFuncSetAttribute(render_kernel_v2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    if (const char* bv = getenv("RT_B200_BVH")) ctx->bvh_builder = strcmp(bv, "host") == 0 ? 1 : (strcmp(bv, "device") == 0 ? 2 : 0);
+    if (const char* bv = getenv("RT_B200_BVH"))
+        ctx->bvh_builder = strcmp(bv, "host") == 0 ? 1 : (strcmp(bv, "device") == 0 ? 2 : (strcmp(bv, "lbvh") == 0 ? 3 : 0));
     if (const char* kv = getenv("RT_B200_KERNEL"))
         ctx->kernel_version = strcmp(kv, "v1") == 0 ? 1 : (strcmp(kv, "wf") == 0 ? 3 : (strcmp(kv, "v3") == 0 ? 4 : 2));
     // v3 parks one path context per lane in shared memory: 23.5 KB per block, three blocks per SM
@@ -1047,7 +1048,8 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
         b.stage_off = stage.add(bytes);
         blocks.push_back(b);
     };
-    const size_t node_skip = device_build ? (size_t)(sc->n_world - 1) * 64 : 0;
+    // device path: n - 1 radix-tree slots + room for the SAH top tree over at most kMaxClusters clusters
+    const size_t node_skip = device_build ? ((size_t)(sc->n_world - 1) + rtlbvh::kMaxClusters) * 64 : 0;
 #define UP(vec, field) add_block(vec.data(), vec.size() * sizeof(vec[0]), 0, (const void**)&S.field);
 #define UPW(vec, field, type, rec_bytes) add_block(vec.data(), vec.size() * sizeof(vec[0]), world_count[type] * (size_t)(rec_bytes), (const void**)&S.field);
     add_block(nodes.data(), device_build ? 0 : nodes.size() * sizeof(float4), node_skip, (const void**)&S.nodes);
@@ -1086,7 +1088,7 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
         *b.field = ctx->arena + b.off;
     }
     uint32_t n_nodes = (uint32_t)bvh.nodes.size(), depth = bvh.depth, leaves = bvh.leaves;
-    int root = bvh.root;
+    int root = bvh.root, device_nodes = 0;
     if (!device_build) {
         CU(ctx, cudaMemcpyAsync(ctx->arena, ctx->staging, plan.size, cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1114,12 +1116,14 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
         if ((size_t)sc->n_triangles * sizeof(rt_triangle) >= 4 * rtlbvh::kCopyChunk || (size_t)sc->n_quads * sizeof(rt_quad) >= 4 * rtlbvh::kCopyChunk ||
             (size_t)sc->n_spheres * sizeof(rt_sphere) >= 4 * rtlbvh::kCopyChunk)
             CU(ctx, ctx->copy_ring.init());
-        CU(ctx, rtlbvh::build_on_device(sc, ctx->scratch, L, T, ctx->stream, ctx->copy_ring, ctx->device, br));
+        CU(ctx, rtlbvh::build_on_device(sc, ctx->scratch, L, T, ctx->stream, ctx->copy_ring, ctx->device, ctx->bvh_builder != 3, br));
         n_nodes = br.nodes;
         depth = br.depth;
         leaves = br.leaves;
-        root = 0;
+        root = br.root;
+        device_nodes = sc->n_world - 1 + (int)br.top_nodes;
         ctx->stats.device_build_ms = br.ms_build + br.ms_emit;
+        ctx->stats.device_top_ms = br.ms_top;
         ctx->stats.device_copy_in_ms = br.ms_copy_in;
         if (depth >= (uint32_t)STACK_SIZE - 2) {
             *too_deep = true;
@@ -1128,7 +1132,7 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
     }
     ctx->stats.bvh_on_device = device_build ? 1 : 0;
     S.root = root;
-    S.n_nodes = device_build ? sc->n_world - 1 : (int)bvh.nodes.size();
+    S.n_nodes = device_build ? device_nodes : (int)bvh.nodes.size();
     S.n_world = sc->n_world;
     S.n_media = sc->n_media;
     S.n_lights = sc->n_lights;
@@ -1152,8 +1156,8 @@ extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
     if (ctx->pending_async) { CU(ctx, cudaStreamSynchronize(ctx->stream)); ctx->pending_async = false; }
     free_scene(ctx);
     // which path: host (bake + binned SAH on the CPU) or device (csrc/bvh_device.cuh)
-    const bool device_build = sc->n_world >= kDeviceBuildMin && (ctx->bvh_builder == 2 || (ctx->bvh_builder == 0 && sc->n_world >= kDeviceBuildAuto));
-    ctx->stats.device_build_ms = ctx->stats.device_copy_in_ms = 0;
+    const bool device_build = sc->n_world >= kDeviceBuildMin && (ctx->bvh_builder >= 2 || (ctx->bvh_builder == 0 && sc->n_world >= kDeviceBuildAuto));
+    ctx->stats.device_build_ms = ctx->stats.device_copy_in_ms = ctx->stats.device_top_ms = 0;
     bool too_deep = false;
     rc = upload_scene_impl(ctx, sc, device_build, &too_deep);
     if (rc == RT_OK && too_deep) rc = upload_scene_impl(ctx, sc, false, &too_deep);  // degenerate input: the SAH tree is shallow
@@ -1164,7 +1168,7 @@ extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
 // 0 auto, 1 host SAH, 2 device LBVH: which builder the next rt_upload_scene uses
 extern "C" int rt_set_bvh_builder(rt_ctx* ctx, int32_t mode) {
     if (!ctx) return RT_ERR_INVALID;
-    if (mode < 0 || mode > 2) return fail(ctx, RT_ERR_INVALID, "rt_set_bvh_builder: mode %d (0 auto, 1 host, 2 device)", mode);
+    if (mode < 0 || mode > 3) return fail(ctx, RT_ERR_INVALID, "rt_set_bvh_builder: mode %d (0 auto, 1 host, 2 device, 3 device without the SAH top)", mode);
     ctx->bvh_builder = mode;
     return RT_OK;
 }

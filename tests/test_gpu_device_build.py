@@ -19,9 +19,9 @@ from raytracingoneweekendapplication_b200 import capi  # noqa: E402
 sys.path.insert(0, os.path.join(helpers.ROOT, "tools"))
 
 
-def _both(scene, fn):
+def _both(scene, fn, modes=("host", "device")):
     out = []
-    for mode in ("host", "device"):
+    for mode in modes:
         c = capi.Context(0)
         try:
             c.set_bvh_builder(mode)
@@ -73,6 +73,22 @@ def test_large_triangle_soup(built):
     assert (host["prim_id"] >= 0).mean() > 0.5
     # the device path exists to make the upload cheap
     assert ds["device_build_ms"] > 0 and ds["device_build_ms"] < 50
+
+
+@pytest.mark.parametrize("name", ["final", "mesh"])
+def test_pure_lbvh_and_sah_top_levels_agree(scene_of, name):
+    """'device' rebuilds the top of the radix tree with SAH over a cut of a few thousand clusters;
+    'lbvh' keeps the radix tree as it is.  Same records, same closest hits."""
+    sc = scene_of(name)
+
+    def run(c):
+        c.render(160, 120, 3, max_depth=sc.depth, seed=11)
+        return c.accum_download()
+
+    (hyb, hs), (pure, ps) = _both(sc, run, modes=("device", "lbvh"))
+    assert hs["bvh_on_device"] == ps["bvh_on_device"] == 1
+    assert hs["bvh_nodes"] > ps["bvh_nodes"]      # the top tree's nodes come on top of the radix tree's
+    assert np.array_equal(hyb, pure)
 
 
 def test_auto_mode_keeps_small_scenes_on_the_host(ctx, scene_of):

@@ -103,7 +103,7 @@ def main():
                           "render_ms": round(best, 2), "msamples_s": round(w * h * spp / best / 1e3, 1),
                           "primary_hit_fraction": round(float((aov["prim_id"] >= 0).mean()), 4),
                           "builder": mode, "on_device": st["bvh_on_device"], "device_build_ms": round(st["device_build_ms"], 3),
-                          "device_copy_in_ms": round(st["device_copy_in_ms"], 3), "bvh_leaves": st["bvh_leaves"]}), flush=True)
+                          "device_copy_in_ms": round(st["device_copy_in_ms"], 3), "device_top_ms": round(st["device_top_ms"], 3), "bvh_leaves": st["bvh_leaves"]}), flush=True)
         ctx.close()
 
 
