@@ -284,10 +284,11 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene);
 /* Which builder rt_upload_scene uses (replaces bvh.h:13-45 either way).
  *   1 host:   transforms baked, binned-SAH BVH2 and device records built on the CPU (best tree)
  *   2 device: raw arrays copied as they are; LBVH (Morton sort + radix tree) and device records
- *             built by CUDA kernels, the top levels of the tree rebuilt with SAH on the host over a
- *             few thousand clusters: ~100x faster upload for million-primitive scenes
+ *             built by CUDA kernels; subtrees of <= 128 primitives rebuilt with SAH (one warp each)
+ *             and the top levels rebuilt with SAH on the host over a few thousand clusters:
+ *             ~40x faster upload for million-primitive scenes, tree within a few % of the host's
  *   3 device, without the SAH top levels (pure LBVH; for comparison)
- *   0 auto:   device from 2^20 primitives up (environment RT_B200_BVH=host|device overrides at rt_create)
+ *   0 auto:   device from 2^16 primitives up (environment RT_B200_BVH=host|device|lbvh overrides at rt_create)
  * Images do not depend on the choice (same records bit for bit, closest hit is tree-independent)
  * except where two primitives are hit at exactly the same t. */
 int rt_set_bvh_builder(rt_ctx* ctx, int32_t mode);

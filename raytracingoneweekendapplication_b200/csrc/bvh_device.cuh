@@ -64,12 +64,12 @@ struct Scratch {
     unsigned long long *key_in, *key_out;  // Morton codes
     uint32_t *val_in, *val_out;            // primitive index
     uint32_t *flag, *scan, *rank_at;       // per sorted position
-    float* cost;                           // per internal node: SAH cost (aliases `flag`, which is dead after the rank passes)
+    float* cost;                           // per internal node: SAH cost of its best completion
     int *left, *right, *parent_int, *parent_leaf, *range_first;
     float4 *nbox_lo, *nbox_hi;             // per internal node; lo.w = count bits, hi.w = type mask | height << 8
     unsigned* visit;
     unsigned* bounds;                      // 6 ordered-uint floats: centroid min xyz, max xyz
-    unsigned* counters;                    // [0] nodes emitted, [1] leaves, [2] height of the root
+    unsigned* counters;                    // [0] nodes emitted, [1] leaves, [2] height of the root, [3] clusters of the cut, [4] rebuilt clusters, [5] their tallest
     void* cub_temp;
     size_t cub_temp_bytes;
 };
@@ -83,7 +83,7 @@ __device__ __forceinline__ float unordered(unsigned u) { return __uint_as_float(
 __global__ void init_kernel(Scratch W) {
     if (threadIdx.x < 3) W.bounds[threadIdx.x] = 0xffffffffu;
     else if (threadIdx.x < 6) W.bounds[threadIdx.x] = 0u;
-    if (threadIdx.x < 4) W.counters[threadIdx.x] = 0u;
+    if (threadIdx.x < 8) W.counters[threadIdx.x] = 0u;
 }
 
 __global__ void __launch_bounds__(256) bounds_kernel(Scratch W) {
@@ -265,6 +265,9 @@ __global__ void __launch_bounds__(256) fit_kernel(Scratch W) {
 // primitives of one type).  Nodes below such a subtree root are never referenced.
 __device__ __forceinline__ bool collapsible(const NodeInfo& v) { return v.as_leaf; }
 
+constexpr float kClusterTravCost = 1.0f;  // the host builder's rtbvh::Tuning::trav_cost (its cost is normalised by the parent's area)
+#include "bvh_cluster_sah.cuh"
+
 __global__ void __launch_bounds__(256) nodes_kernel(Scratch W, Targets T) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= W.n - 1) return;
@@ -380,7 +383,7 @@ struct ScratchPlan {
 struct Layout {
     size_t world, spheres, quads, triangles, xforms;
     size_t box_lo, box_hi, key_in, key_out, val_in, val_out, flag, scan, rank_at, left, right, parent_int, parent_leaf, range_first,
-        nbox_lo, nbox_hi, visit, bounds, counters, cub_temp, clusters;
+        nbox_lo, nbox_hi, visit, bounds, counters, cub_temp, clusters, cost;
     size_t cub_temp_bytes, total;
 };
 
@@ -396,7 +399,7 @@ inline Layout plan_scratch(const rt_scene_desc* sc) {
     L.box_lo = p.add(n * 16); L.box_hi = p.add(n * 16);
     L.key_in = p.add(n * 8); L.key_out = p.add(n * 8);
     L.val_in = p.add(n * 4); L.val_out = p.add(n * 4);
-    L.flag = p.add(n * 4); L.scan = p.add(n * 4); L.rank_at = p.add(n * 4);
+    L.flag = p.add(n * 4); L.scan = p.add(n * 4); L.rank_at = p.add(n * 4); L.cost = p.add(n * 4);
     L.left = p.add(n * 4); L.right = p.add(n * 4); L.parent_int = p.add(n * 4); L.parent_leaf = p.add(n * 4); L.range_first = p.add(n * 4);
     L.nbox_lo = p.add(n * 16); L.nbox_hi = p.add(n * 16);
     L.visit = p.add(n * 4);
@@ -477,6 +480,7 @@ struct BuildResult {
     unsigned nodes = 0, leaves = 0, depth = 0;
     int root = 0;            // index of the root node in the node array
     unsigned top_nodes = 0;  // nodes of the SAH top tree appended after the n - 1 radix-tree slots (0: pure LBVH)
+    unsigned rebuilt_clusters = 0;
     float ms_copy_in = 0, ms_build = 0, ms_emit = 0, ms_top = 0;
 };
 
@@ -508,7 +512,7 @@ inline cudaError_t build_on_device(const rt_scene_desc* sc, unsigned char* scrat
     W.key_in = (unsigned long long*)at(L.key_in); W.key_out = (unsigned long long*)at(L.key_out);
     W.val_in = (uint32_t*)at(L.val_in); W.val_out = (uint32_t*)at(L.val_out);
     W.flag = (uint32_t*)at(L.flag); W.scan = (uint32_t*)at(L.scan); W.rank_at = (uint32_t*)at(L.rank_at);
-    W.cost = (float*)at(L.flag);
+    W.cost = (float*)at(L.cost);
     W.left = (int*)at(L.left); W.right = (int*)at(L.right); W.parent_int = (int*)at(L.parent_int);
     W.parent_leaf = (int*)at(L.parent_leaf); W.range_first = (int*)at(L.range_first);
     W.nbox_lo = (float4*)at(L.nbox_lo); W.nbox_hi = (float4*)at(L.nbox_hi);
@@ -522,29 +526,40 @@ inline cudaError_t build_on_device(const rt_scene_desc* sc, unsigned char* scrat
     morton_kernel<<<gn, tpb, 0, stream>>>(W);
     size_t tb = W.cub_temp_bytes;
     if ((e = cub::DeviceRadixSort::SortPairs(W.cub_temp, tb, W.key_in, W.key_out, W.val_in, W.val_out, n, 0, 63, stream)) != cudaSuccess) return e;
+    karras_kernel<<<gi, tpb, 0, stream>>>(W);
+    fit_kernel<<<gn, tpb, 0, stream>>>(W);
+    if (hybrid_top) {
+        // SAH rebuild of every subtree of 3..kClusterMax primitives (one warp each); permutes the
+        // sorted order inside the clusters, so it runs before the typed ranks are taken
+        int* roots = (int*)W.scan;  // free until the rank passes
+        cluster_roots_kernel<<<gi, tpb, 0, stream>>>(W, roots, W.counters + 4);
+        // the grid is sized for the worst case (every cluster has 3 primitives); surplus warps leave at once
+        const int max_clusters = n / 3 + 1;
+        cluster_sah_kernel<<<(max_clusters + kClusterWarps - 1) / kClusterWarps, 32 * kClusterWarps, 0, stream>>>(W, roots, W.counters + 4, W.counters + 5);
+    }
     for (unsigned t = 0; t < 4; t++) {
         flag_kernel<<<gn, tpb, 0, stream>>>(W, t);
         tb = W.cub_temp_bytes;
         if ((e = cub::DeviceScan::ExclusiveSum(W.cub_temp, tb, W.flag, W.scan, n, stream)) != cudaSuccess) return e;
         pick_rank_kernel<<<gn, tpb, 0, stream>>>(W, t);
     }
-    karras_kernel<<<gi, tpb, 0, stream>>>(W);
-    fit_kernel<<<gn, tpb, 0, stream>>>(W);
     cudaEventRecord(ev[2], stream);
     nodes_kernel<<<gi, tpb, 0, stream>>>(W, T);
     prims_kernel<<<gn, tpb, 0, stream>>>(W, T);
     cudaEventRecord(ev[3], stream);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    unsigned c[4] = {0, 0, 0, 0};
+    unsigned c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if ((e = cudaMemcpyAsync(c, W.counters, sizeof c, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
     out.nodes = c[0];
     out.leaves = c[1];
-    out.depth = c[2];
+    const unsigned rebuilt_tallest = c[5];
+    out.depth = c[2] + rebuilt_tallest;  // an upper bound: radix-tree height + the tallest rebuilt cluster
+    out.rebuilt_clusters = c[4];
     out.root = 0;
     out.top_nodes = 0;
     // ---- SAH top levels over the cut of the radix tree ------------------------------------------
-    unsigned max_count = std::max<unsigned>(64u, (unsigned)(2ull * (unsigned long long)n / (kMaxClusters / 2)));
+    unsigned max_count = std::max<unsigned>((unsigned)kClusterMax, (unsigned)(2ull * (unsigned long long)n / (kMaxClusters / 2)));
     if (const char* ev_c = getenv("RT_B200_CLUSTER")) max_count = std::max(2, atoi(ev_c));  // tuning experiments
     if (hybrid_top && (unsigned)n > 4 * max_count) {
         auto t0 = std::chrono::steady_clock::now();
@@ -582,7 +597,7 @@ inline cudaError_t build_on_device(const rt_scene_desc* sc, unsigned char* scrat
                 if ((e = cudaMemcpy(T.nodes + 4 * (size_t)base, top.nodes.data(), top.nodes.size() * sizeof(rtbvh::Node), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
                 out.root = top.root + base;
                 out.top_nodes = (unsigned)top.nodes.size();
-                out.depth = top.depth + tallest;
+                out.depth = top.depth + tallest + rebuilt_tallest;
                 out.nodes += out.top_nodes;
             }
         }

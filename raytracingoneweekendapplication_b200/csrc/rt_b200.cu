@@ -604,10 +604,10 @@ struct rt_ctx {
 };
 
 // From this many primitives on, RT_B200_BVH=auto builds on the device: the host SAH build costs
-// ~0.45 s per million triangles, the device path a few milliseconds, and the LBVH it produces
-// renders measurably slower per sample (numbers in DESIGN.md) -- above this size an upload is worth
-// more than 100 samples per pixel of a 1080p frame.
-constexpr int kDeviceBuildAuto = 1 << 20;
+// ~0.4 ms per thousand triangles (30 ms at this size), the device path ~2 ms, and with the
+// per-cluster SAH rebuild and the SAH top levels the device-built tree traces within -1...-12 % of
+// the host's.  Every BASELINE scene is smaller and keeps the host tree.
+constexpr int kDeviceBuildAuto = 1 << 16;
 constexpr int kDeviceBuildMin = 8;
 
 static int fail(rt_ctx* ctx, int code, const char* fmt, ...) {

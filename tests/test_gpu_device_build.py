@@ -50,10 +50,10 @@ def test_primary_hits_and_images_match_the_host_path(scene_of, name):
     assert ds["bvh_on_device"] == 1 and ds["bvh_nodes"] > 0 and 0 < ds["bvh_depth"] < 62
     tie = host[0]["prim_id"] != dev[0]["prim_id"]
     # the ids may differ ONLY where two primitives are hit at exactly the same t (kitchen_sink has
-    # coincident faces): t is equal everywhere, bit for bit
+    # coincident faces, the Cornell box shared edges): t is equal everywhere, bit for bit
     assert np.array_equal(host[0]["t"], dev[0]["t"]), f"{name}: primary t differs"
     assert tie.mean() <= 0.01, f"{name}: primary ids differ on {tie.sum()} pixels"
-    if name != "kitchen_sink":
+    if name not in ("kitchen_sink", "cornell"):
         assert not tie.any()
     assert np.array_equal(host[0]["normal"][~tie], dev[0]["normal"][~tie])
     same_px = (host[1] == dev[1]).all(axis=-1)
@@ -77,8 +77,9 @@ def test_large_triangle_soup(built):
 
 @pytest.mark.parametrize("name", ["final", "mesh"])
 def test_pure_lbvh_and_sah_top_levels_agree(scene_of, name):
-    """'device' rebuilds the top of the radix tree with SAH over a cut of a few thousand clusters;
-    'lbvh' keeps the radix tree as it is.  Same records, same closest hits."""
+    """'device' rebuilds the radix tree's small subtrees (one warp per cluster) and its top levels
+    (host, over a cut of a few thousand clusters) with SAH; 'lbvh' keeps the radix tree as it is.
+    Same records, same closest hits."""
     sc = scene_of(name)
 
     def run(c):
@@ -87,7 +88,7 @@ def test_pure_lbvh_and_sah_top_levels_agree(scene_of, name):
 
     (hyb, hs), (pure, ps) = _both(sc, run, modes=("device", "lbvh"))
     assert hs["bvh_on_device"] == ps["bvh_on_device"] == 1
-    assert hs["bvh_nodes"] > ps["bvh_nodes"]      # the top tree's nodes come on top of the radix tree's
+    assert hs["bvh_nodes"] != ps["bvh_nodes"]     # different trees ...
     assert np.array_equal(hyb, pure)
 
 
