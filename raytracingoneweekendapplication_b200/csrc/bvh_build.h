@@ -60,6 +60,7 @@ constexpr int kAllAxes = 256;
 struct Tuning {
     int max_leaf = 4;       // primitives per leaf (<= 8, the link encoding has 3 count bits)
     float trav_cost = 1.0f; // cost of one node visit relative to a sphere test
+    size_t shortcut_min = 4096;  // scenes with more primitives than this take the build-time shortcuts (fewer bins for small ranges, pairs become leaves unexamined)
 };
 
 // One builder instance fills one Result for the index range it is given; `ids` is shared
@@ -104,13 +105,13 @@ class Builder {
         // average) more than one test -- never worth evaluating (and it halves the node count)
         // (only for big scenes, where build time is end-to-end time; small scenes such as the
         // Cornell box measurably prefer the full SAH decision: 1850 vs 1660 Msamples/s)
-        if (n == 2 && tune.max_leaf >= 2 && P.size() > 1024 && single_type(a, b)) return false;
+        if (n == 2 && tune.max_leaf >= 2 && P.size() > tune.shortcut_min && single_type(a, b)) return false;
 
         int best_axis = -1, best_bin = -1;
         float best_cost = FLT_MAX;
         // small ranges of BIG scenes use fewer bins (most of 16 would be empty and the fixed cost per
         // node dominates the build); small scenes always get the full resolution
-        const int nbins = P.size() <= 1024 ? kBins : (n < 8 ? 4 : (n < 32 ? 8 : kBins));
+        const int nbins = P.size() <= tune.shortcut_min ? kBins : (n < 8 ? 4 : (n < 32 ? 8 : kBins));
         const float parent_area = std::max(bounds.area(), 1e-30f);
         // Large ranges are binned along the longest centroid axis only (the other axes are tried
         // if that one offers no split); ranges of <= kAllAxes primitives get the full 3-axis search.
