@@ -533,8 +533,9 @@ inline cudaError_t build_on_device(const rt_scene_desc* sc, unsigned char* scrat
         // sorted order inside the clusters, so it runs before the typed ranks are taken
         int* roots = (int*)W.scan;  // free until the rank passes
         cluster_roots_kernel<<<gi, tpb, 0, stream>>>(W, roots, W.counters + 4);
-        // clusters are disjoint and two sibling clusters hold more than kClusterMax primitives together, so
-        // there are at most 2n / kClusterMax of them; the grid is sized for twice that, surplus warps leave at once
+        // a balanced tree has about 2n / kClusterMax clusters; the grid is sized for twice that and surplus
+        // warps leave at once.  A degenerate (chain-like) radix tree can have up to n / 3 small clusters: the
+        // ones beyond the grid simply keep their radix subtree, which is a valid tree either way
         const int max_clusters = 4 * (n / kClusterMax) + 4;
         cluster_sah_kernel<<<(max_clusters + kClusterWarps - 1) / kClusterWarps, 32 * kClusterWarps, 0, stream>>>(W, roots, W.counters + 4, W.counters + 5);
     }
