@@ -142,6 +142,24 @@ __global__ void __launch_bounds__(32 * kClusterWarps) cluster_sah_kernel(Scratch
         total_cost = warp_sum(total_cost);
         mask = __reduce_or_sync(0xffffffffu, mask);
         const float parent_area = fmaxf(box_area(blo, bhi), 1e-30f);
+        // ---- two primitives (a third of all ranges): the only split is one and one, no bins needed ----
+        if (n == 2) {
+            const int e0 = S.perm[lo], e1 = S.perm[lo + 1];
+            float l0[3], h0[3], l1[3], h1[3];
+            for (int k = 0; k < 3; k++) { l0[k] = S.lo[k][e0]; h0[k] = S.hi[k][e0]; l1[k] = S.lo[k][e1]; h1[k] = S.hi[k][e1]; }
+            const float split_cost = kClusterTravCost + (box_area(l0, h0) * prim_cost(S.type[e0]) + box_area(l1, h1) * prim_cost(S.type[e1])) / parent_area;
+            const bool pair_leaf = kMaxLeaf >= 2 && __popc(mask) == 1 && total_cost <= split_cost;
+            if (lane == 0) {
+                W.nbox_lo[slot] = make_float4(blo[0], blo[1], blo[2], __uint_as_float(2u));
+                W.nbox_hi[slot] = make_float4(bhi[0], bhi[1], bhi[2], __uint_as_float(mask | (pair_leaf ? 0x80u : 0u)));
+                W.range_first[slot] = a + lo;
+                W.parent_leaf[a + lo] = slot;
+                W.parent_leaf[a + lo + 1] = slot;
+                W.left[slot] = ~(a + lo);
+                W.right[slot] = ~(a + lo + 1);
+            }
+            continue;
+        }
         // ---- bins ----------------------------------------------------------------------------------
         for (int j = lane; j < 3 * kSahBins; j += 32) {
             const int ax = j / kSahBins, b = j % kSahBins;
