@@ -32,13 +32,14 @@ int main(int argc, char** argv) {
     }
     if (argc > 5) { cam.image_width = std::atoi(argv[4]); cam.aspect_ratio = double(cam.image_width) / std::atoi(argv[5]); }
     if (argc > 6) cam.samples_per_pixel = std::atoi(argv[6]);
-    // download-side additions: --checkpoint FILE [--every N] [--stop-after N] [--linear FILE.exr|.pfm]
+    // additions: --checkpoint FILE [--every N] [--stop-after N] [--linear FILE.exr|.pfm] [--nee 0|1]
     for (int i = 7; i + 1 < argc; i += 2) {
         std::string k = argv[i];
         if (k == "--checkpoint") cam.checkpoint_path = argv[i + 1];
         else if (k == "--every") cam.checkpoint_every_spp = std::atoi(argv[i + 1]);
         else if (k == "--stop-after") cam.stop_after_spp = std::atoi(argv[i + 1]);
         else if (k == "--linear") cam.linear_name = argv[i + 1];
+        else if (k == "--nee") cam.next_event_estimation = std::atoi(argv[i + 1]) != 0;
         else { std::cerr << "unknown option " << k << std::endl; return 1; }
     }
     cam.image_name = out.c_str();

@@ -214,6 +214,11 @@ typedef enum rt_shard_mode {
                                  (progressive rendering: pass a fresh spp_begin each time)   */
 #define RT_FLAG_ASYNC 2u      /* enqueue on `stream` and return; rt_sync() / rt_download wait */
 #define RT_FLAG_STATS 4u      /* count rays / node visits / prim tests (slower kernel variant) */
+#define RT_FLAG_NEE 8u        /* opt-in next-event estimation: lambertian and isotropic vertices sample the quad
+                                 emitters of the scene directly (shadow ray, media transmittance), weighted with the
+                                 density of the reference's own direction sampler, so the CONVERGED image is the one
+                                 the reference converges to; individual samples differ, noise is lower.  Ignored when
+                                 the scene has no quad emitter or was uploaded by the device builder. */
 
 typedef struct rt_render_params {
     uint32_t struct_size;

@@ -225,7 +225,7 @@ constexpr int kTravThreshold = RT_TRAV_THRESHOLD;
 constexpr int kDescendDiv = RT_DESCEND_DIV;
 enum : int { LANE_IDLE = 0, LANE_TRAVERSE = 1, LANE_SHADE = 2 };
 
-template <bool STATS, bool LITE>
+template <bool STATS, bool LITE, bool NEE = false>
 __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A,
                                                         unsigned long long* __restrict__ accum,
                                                         unsigned long long* __restrict__ counters, Stats* __restrict__ gstats) {
@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __g
     ray.time = 0;
     V3 L = v3(0, 0, 0), T = v3(1, 1, 1);
     uint32_t bounce = 0, origin_prim = PRIM_NONE;
+    float nee_pdf = 0.0f;  // NEE: > 0 when the previous vertex sampled the listed emitters directly: the density of the direction it scattered into
     Trav tr;
     StackEntry stack[STACK_SIZE];
     tr.cur = LINK_DONE;
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __g
                     T = v3(1, 1, 1);
                     bounce = 0;
                     origin_prim = PRIM_NONE;
+                    nee_pdf = 0.0f;
                     tr.init(S, kInf);
                     state = tr.done() ? LANE_SHADE : LANE_TRAVERSE;
                     if (STATS) { st.samples++; st.rays++; seg_steps = n_leaf = 0; }
@@ -382,6 +384,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __g
                     sf.u = sf.v = 0.0f;
                     sf.material = md.material;
                     sf.prim_id = -1;
+                    sf.nee_light = 0;
                     origin_prim = PRIM_NONE;
                 } else {
                     complete_hit(S, ray, hit, sf, false);
@@ -393,11 +396,27 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __g
                 V3 att, emitted;
                 Ray next;
                 const bool scattered = shade_surface(S, m, ray, sf, u4, emitted, att, next);
+                // NEE: a listed emitter reached from a vertex that also sampled the emitters directly shares the
+                // estimate with that sample (balance heuristic)
+                if (NEE && nee_pdf > 0.0f && medium < 0 && sf.nee_light > 0) {
+                    const float d2 = dot(ray.d, ray.d);
+                    const float cos_y = fabsf(dot(ray.d, v3(S.nee_lights[sf.nee_light - 1].n))) * rsqrtf(d2);
+                    const float p_light = light_density(S, sf.t * sf.t * d2, fmaxf(cos_y, 1e-20f));
+                    emitted = (nee_pdf / (nee_pdf + p_light)) * emitted;
+                }
                 L = L + T * emitted;
                 if (!scattered) {
                     done = true;
                 } else {
                     if (!LITE && S.n_lights > 0) L = L + T * att * point_lighting(S, sf.p, sf.normal);
+                    if (NEE) {
+                        nee_pdf = 0.0f;
+                        if (S.n_nee_lights > 0 && (m.type == RT_MAT_LAMBERTIAN || m.type == RT_MAT_ISOTROPIC)) {
+                            const bool iso = m.type == RT_MAT_ISOTROPIC;
+                            nee_pdf = scatter_density(normalize(next.d), sf.normal, iso);
+                            L = L + T * att * nee_direct(S, sf.p, sf.normal, iso, origin_prim, ray.time, rng.draw(bounce, RS_NEE), &counters[1]);
+                        }
+                    }
                     T = T * att;
                     ray = next;
                     bounce++;
@@ -685,6 +704,8 @@ extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
     cudaFuncSetAttribute(render_kernel_v2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel_v2<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel_v2<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     if (const char* bv = getenv("RT_B200_BVH"))
         ctx->bvh_builder = strcmp(bv, "host") == 0 ? 1 : (strcmp(bv, "device") == 0 ? 2 : (strcmp(bv, "lbvh") == 0 ? 3 : 0));
     if (const char* kv = getenv("RT_B200_KERNEL"))
@@ -957,7 +978,33 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
             return (PT_TRI << 28) | (uint32_t)(world_count[PT_TRI] + tri_sh.size() / 3 - 1);
         }
     };
-    for (uint32_t id : bvh.order) emit(baked[id]);
+    // quads with an emissive material are also listed for the opt-in next-event estimation (host path only)
+    std::vector<DevNeeLight> nee_lights;
+    double nee_area = 0.0;
+    for (uint32_t id : bvh.order) {
+        const BakedPrim& b = baked[id];
+        const uint32_t packed = emit(b);
+        if (b.dev_type != PT_QUAD || b.material < 0) continue;
+        const rt_material& m = sc->materials[b.material];
+        if (m.type != RT_MAT_DIFFUSE_LIGHT && m.type != RT_MAT_EMISSIVE_LIGHT) continue;
+        const D3 nn = dcross(b.b, b.c);
+        const double area = std::sqrt(ddot(nn, nn));
+        if (!(area > 0.0)) continue;
+        DevNeeLight lt;
+        std::memset(&lt, 0, sizeof lt);
+        lt.Q[0] = (float)b.a.x; lt.Q[1] = (float)b.a.y; lt.Q[2] = (float)b.a.z;
+        lt.u[0] = (float)b.b.x; lt.u[1] = (float)b.b.y; lt.u[2] = (float)b.b.z;
+        lt.v[0] = (float)b.c.x; lt.v[1] = (float)b.c.y; lt.v[2] = (float)b.c.z;
+        lt.n[0] = (float)(nn.x / area); lt.n[1] = (float)(nn.y / area); lt.n[2] = (float)(nn.z / area);
+        lt.area = (float)area;
+        lt.tex = m.texture;
+        nee_area += area;
+        lt.cdf = (float)nee_area;  // normalised below
+        nee_lights.push_back(lt);
+        quad_sh[(packed & 0x0fffffffu) - world_count[PT_QUAD]].w = (int)nee_lights.size();
+    }
+    for (DevNeeLight& lt : nee_lights) lt.cdf = (float)(lt.cdf / nee_area);
+    if (!nee_lights.empty()) nee_lights.back().cdf = 1.0f;
     for (int i = 0; i < sc->n_boundary_refs; i++) boundary_packed[i] = emit(baked[first_boundary + i]);
 
     // ---- tables ---------------------------------------------------------------------------
@@ -1059,7 +1106,7 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
     UPW(sph_sh, sph_sh, PT_SPHERE, 16) UPW(msph_sh, msph_sh, PT_MSPHERE, 16) UPW(quad_sh, quad_sh, PT_QUAD, 16) UPW(tri_sh, tri_sh, PT_TRI, 48)
     UP(xrot, xrot) UP(media, media)
     UP(boundary_packed, boundary) UP(mats, mats) UP(texs, texs) UP(images, images) UP(perlin_vec, perlin_vec)
-    UP(perlin_perm, perlin_perm) UP(lights, lights)
+    UP(perlin_perm, perlin_perm) UP(lights, lights) UP(nee_lights, nee_lights)
 #undef UP
 #undef UPW
     if (plan.size > ctx->arena_cap) {
@@ -1137,6 +1184,8 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
     S.n_world = sc->n_world;
     S.n_media = sc->n_media;
     S.n_lights = sc->n_lights;
+    S.n_nee_lights = (int)nee_lights.size();
+    S.nee_total_area = (float)nee_area;
     ctx->camera = sc->camera;
     ctx->scene_lite = tri.empty() && world_count[PT_TRI] == 0 && sc->n_lights == 0 && !(sc->camera.defocus_angle > 0);
     ctx->cam_w = ctx->cam_h = 0;
@@ -1428,7 +1477,10 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
                 cudaFuncSetAttribute(render_kernel_v2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
                 cudaFuncSetAttribute(render_kernel_v2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             }
-            if (stats) render_kernel_v2<true, false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            const bool nee = (p->flags & RT_FLAG_NEE) != 0 && ctx->scene.n_nee_lights > 0;
+            if (nee && lite) render_kernel_v2<false, true, true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            else if (nee) render_kernel_v2<false, false, true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            else if (stats) render_kernel_v2<true, false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
             else if (lite) render_kernel_v2<false, true><<<grid, 256, dummy, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
             else render_kernel_v2<false, false><<<grid, 256, dummy, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
         }

@@ -56,6 +56,18 @@ struct DevMedium {  // 48 B
     float bmin[3];
     float bmax_pad;
 };
+// A quad emitter the opt-in next-event estimation samples: world-space
+// corner and edges, area, emission texture, and the running share of the total emitter area.
+struct DevNeeLight {  // 64 B
+    float Q[3];
+    float area;
+    float u[3];
+    int tex;
+    float v[3];
+    float cdf;  // sum of the areas up to and including this light / total area
+    float n[3];
+    int pad;
+};
 struct DevLight {
     float pos[3];
     float size;
@@ -91,6 +103,9 @@ struct DevScene {
     const unsigned char* perlin_perm;  // 768 per perlin: perm_x, perm_y, perm_z
     const DevLight* lights;
     int n_lights;
+    const DevNeeLight* nee_lights;  // RT_FLAG_NEE: quads with an emissive material
+    int n_nee_lights;
+    float nee_total_area;
     // camera (Camera.txt:136-175, evaluated in double on the host)
     float center[3], dir00[3], du[3], dv[3], disk_u[3], disk_v[3];
     float background[3];
@@ -137,7 +152,7 @@ __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 //   stream 16       scatter: x,y,z = random_unit_vector's cube point, w = dielectric test
 //   stream 32 + k   media 4k..4k+3: one free-flight uniform each
 // ---------------------------------------------------------------------------------
-constexpr uint32_t RS_CAMERA = 0, RS_DEFOCUS = 1, RS_SCATTER = 16, RS_MEDIUM = 32;
+constexpr uint32_t RS_CAMERA = 0, RS_DEFOCUS = 1, RS_SCATTER = 16, RS_NEE = 24, RS_MEDIUM = 32;
 
 #ifndef RT_PHILOX_ATTR
 #define RT_PHILOX_ATTR __forceinline__  // out of line costs 10 % on C5 (call ABI spills); measured
@@ -583,6 +598,7 @@ struct Surface {
     float u, v;
     int material;
     int prim_id;
+    int nee_light;  // > 0: this surface is emitter number nee_light - 1 of the next-event list
     bool front;
 };
 
@@ -621,6 +637,7 @@ __device__ __forceinline__ void complete_hit(const DevScene& S, const Ray& ray, 
     V3 outward;
     sf.u = hit.u;
     sf.v = hit.v;
+    sf.nee_light = 0;
     if (type == PT_SPHERE || type == PT_MSPHERE) {
         // The accepted sphere hit is re-solved ONCE in double (sphere.h:33-52 verbatim): the
         // FP32 traversal fixes WHICH root of WHICH sphere, the FP64 pass fixes t, p and the
@@ -668,6 +685,7 @@ __device__ __forceinline__ void complete_hit(const DevScene& S, const Ray& ray, 
         int4 sh = __ldg(S.quad_sh + idx);
         sf.material = sh.x;
         sf.prim_id = sh.z;
+        sf.nee_light = sh.w;
     } else {
         const float4* ts = S.tri_sh + 3 * (size_t)idx;
         float4 a = ldg4(ts), b = ldg4(ts + 1), c = ldg4(ts + 2);
@@ -794,6 +812,111 @@ __device__ __noinline__ V3 point_lighting(const DevScene& S, V3 p, V3 normal) {
         }
     }
     return result;
+}
+
+// ---------------------------------------------------------------------------------
+// Next-event estimation (opt-in, RT_FLAG_NEE).
+//
+// The reference estimates L_o = albedo * L_i(w) with ONE direction w drawn from its own
+// sampler: w = n + unit(c), c uniform in the cube [-1,1]^3 (vec3.h:107-115) for a
+// lambertian, w = unit(c) for the isotropic phase function.  The expectation is split here into
+// the part that comes straight from the quad emitters -- estimated by sampling a point ON an
+// emitter and weighting with the density p(w) of the reference's sampler -- and the rest, for which
+// the scattered ray goes on as before but does not collect the emission of a listed emitter it hits
+// next.  Same expectation (the converged image is the reference's), much less variance where the
+// emitters are small.  The two ways of finding an emitter -- the sampled point and the scattered ray
+// that happens to hit it -- are combined with the balance heuristic (weights p_light / (p_light +
+// p_w) and p_w / (p_light + p_w), both densities per steradian), which keeps the light sample's
+// 1 / r^2 bounded for vertices close to an emitter (the Cornell ceiling is one unit above its light).  Density of unit(c) on the sphere: (1/8) * integral_0^R r^2 dr = R^3 / 24 per
+// steradian, R = 1 / max|u_i| the distance to the cube's face; w = unit(n + u) maps the unit
+// sphere around n to directions with dA_u = 4 cos(theta) dw, so p_lambert(w) = R(u)^3 cos(theta) / 6
+// with u = 2 cos(theta) w - n (for a uniform u this is the cosine lobe cos/pi).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float cube_point_density(V3 u) {  // of unit(c), per steradian
+    const float m = fmaxf(fabsf(u.x), fmaxf(fabsf(u.y), fabsf(u.z)));
+    const float R = 1.0f / m;
+    return R * R * R * (1.0f / 24.0f);
+}
+// density of the reference's scattering direction `dir` (unit) at a vertex with normal n
+__device__ __forceinline__ float scatter_density(V3 dir, V3 n, bool isotropic) {
+    if (isotropic) return cube_point_density(dir);
+    const float c = dot(dir, n);
+    if (!(c > 0.0f)) return 0.0f;
+    return cube_point_density((2.0f * c) * dir - n) * 4.0f * c;
+}
+// density per steradian with which the emitter sampler proposes the point at squared distance r2 seen under cos_y
+__device__ __forceinline__ float light_density(const DevScene& S, float r2, float cos_y) { return r2 / (cos_y * S.nee_total_area); }
+
+// Probability that a ray survives every constant_medium between tmin and tmax (constant_medium.h:20-53:
+// the free-flight distance is exponential with rate density, times the leaf multiplicity of Q15).
+__device__ __forceinline__ float media_transmittance(const DevScene& S, const Ray& ray, float tmin, float tmax) {
+    const float a = dot(ray.d, ray.d);
+    const float inv_a = 1.0f / a;
+    const float ray_length = sqrtf(a);
+    float optical_depth = 0.0f;
+    for (int m = 0; m < S.n_media; m++) {
+        const DevMedium& md = S.media[m];
+        float t1, t2;
+        if (md.sphere >= 0) {
+            float4 s = ldg4(S.sph + md.sphere);
+            V3 oc = v3(s) - ray.o;
+            float k = dot(ray.d, oc) * inv_a;
+            float r2 = s.w * s.w;
+            float cterm = dot(oc, oc) - r2;
+            if (fabsf(cterm) < 0.125f * r2) {
+                if (!sphere_roots_fp64(S.sph_d + 4 * (size_t)md.sphere, false, ray, t1, t2)) continue;
+            } else {
+                V3 l = fma3(-k, ray.d, oc);
+                float disc = r2 - dot(l, l);
+                if (disc < 0.0f) continue;
+                float sq = sqrtf(disc * inv_a);
+                t1 = k - sq;
+                t2 = k + sq;
+            }
+            if (!(t2 > t1 + 0.0001f)) continue;
+        } else {
+            if (!boundary_pair_generic(S, md.bfirst, md.bcount, ray, inv_a, t1, t2)) continue;
+        }
+        if (t1 < tmin) t1 = tmin;
+        if (t2 > tmax) t2 = tmax;
+        if (t1 >= t2) continue;
+        if (t1 < 0.0f) t1 = 0.0f;
+        optical_depth += (t2 - t1) * ray_length * (-1.0f / md.neg_inv_density);
+    }
+    return __expf(-optical_depth);
+}
+
+// The directly-lit part of one lambertian / isotropic scattering event at p: radiance per unit of
+// (throughput * albedo).  `u` = three uniforms (which emitter, where on it).
+__device__ __noinline__ V3 nee_direct(const DevScene& S, V3 p, V3 n, bool isotropic, uint32_t origin_prim, float time, float4 u,
+                                      unsigned long long* overflow_flag) {
+    int k = 0;
+    while (k + 1 < S.n_nee_lights && u.x >= S.nee_lights[k].cdf) k++;
+    const DevNeeLight& lt = S.nee_lights[k];
+    const V3 y = v3(lt.Q) + u.y * v3(lt.u) + u.z * v3(lt.v);
+    const V3 w = y - p;
+    const float r2 = dot(w, w);
+    if (!(r2 > 0.0f)) return v3(0, 0, 0);
+    const float r = sqrtf(r2);
+    const V3 dir = (1.0f / r) * w;
+    const float density = scatter_density(dir, n, isotropic);
+    if (!(density > 0.0f)) return v3(0, 0, 0);
+    const float cos_y = fabsf(dot(dir, v3(lt.n)));  // diffuse_light emits from both faces (material.h:99-101)
+    if (!(cos_y > 0.0f)) return v3(0, 0, 0);
+    Ray sray;
+    sray.o = p;
+    sray.d = dir;
+    sray.time = time;
+    const float tmax = r * (1.0f - 1e-4f);
+    Hit h;
+    int ov = 0;
+    traverse<false>(S, sray, 0.001f, tmax, origin_prim, h, nullptr, &ov);
+    if (ov) atomicAdd(overflow_flag, 1ull);
+    if (h.prim != PRIM_NONE) return v3(0, 0, 0);
+    // Le * p_w / p_light, times the balance-heuristic weight p_light / (p_light + p_w)
+    float weight = density / (light_density(S, r2, cos_y) + density);
+    if (S.n_media > 0) weight *= media_transmittance(S, sray, 0.001f, tmax);
+    return weight * tex_value(S, lt.tex, u.y, u.z, y);
 }
 
 // Camera.txt:177-200 get_ray.  Directions are built relative to the camera centre

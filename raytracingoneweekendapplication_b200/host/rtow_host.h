@@ -1545,6 +1545,9 @@ class camera {
     //                    checkpoint_every_spp samples (0: only when the render stops early)
     //   stop_after_spp   > 0: stop once this many samples are in the frame (an orderly
     //                    interruption: checkpoint written, image of the samples so far)
+    //   next_event_estimation  opt-in: sample the quad emitters directly at diffuse
+    //                    and isotropic vertices (RT_FLAG_NEE); same converged image, far less noise
+    bool next_event_estimation = false;
     std::string linear_name;
     std::string checkpoint_path;
     int checkpoint_every_spp = 0;
@@ -1630,7 +1633,7 @@ class camera {
             if (!checkpoint_path.empty() && checkpoint_every_spp > 0) n = std::min(n, std::max(1, checkpoint_every_spp - since_save));
             p.samples_per_pixel = n;
             p.spp_begin = done;
-            p.flags = fresh ? 0 : RT_FLAG_ACCUMULATE;
+            p.flags = (fresh ? 0 : RT_FLAG_ACCUMULATE) | (next_event_estimation ? RT_FLAG_NEE : 0);
             fresh = false;
             if (rt_render(ctx, &p) != RT_OK) fail("rt_render");
             done += n;

@@ -1,0 +1,79 @@
+"""Opt-in next-event estimation (RT_FLAG_NEE).
+
+The estimator is a different one from the reference's (individual samples differ), but it is built
+to have the SAME expectation: direct light from the quad emitters is sampled on the emitters and
+weighted with the density of the reference's own direction sampler, and the scattered ray does
+not collect a listed emitter's emission a second time.  So the parity gate is gate (b) of the
+converged images — against the images rendered by the UNMODIFIED reference (tests/golden/
+image_*.npz) — reached with far fewer samples, plus a direct NEE-vs-plain comparison."""
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+from raytracingoneweekendapplication_b200 import capi  # noqa: E402
+
+NEE_SCENES = ["cornell", "cornell_smoke", "final", "emissive", "kitchen_sink"]
+
+
+def _halves(ctx, w, h, spp, depth, nee):
+    ctx.render(w, h, spp // 2, max_depth=depth, seed=11, nee=nee)
+    a = ctx.download(spp // 2).astype(np.float64)
+    ctx.render(w, h, spp // 2, max_depth=depth, seed=22, nee=nee)
+    b = ctx.download(spp // 2).astype(np.float64)
+    return a, b
+
+
+@pytest.mark.parametrize("name", NEE_SCENES)
+def test_nee_converges_to_the_reference_image(ctx, scene_of, name):
+    sc = scene_of(name)
+    ctx.upload(sc)
+    g = helpers.golden("image", name)
+    ref, ref_var, ref_spp, depth = g["image"].astype(np.float64), g["var"].astype(np.float64), int(g["spp"]), int(g["depth"])
+    h, w, _ = ref.shape
+    a, b = _halves(ctx, w, h, 8192, depth, nee=True)
+    dev = 0.5 * (a + b)
+    n = h * w
+    sigma_ref = np.sqrt((ref_var / ref_spp).sum(axis=(0, 1))) / n
+    sigma_dev = 0.5 * np.sqrt(((a - b) ** 2).sum(axis=(0, 1))) / n
+    sigma = np.sqrt(sigma_ref ** 2 + sigma_dev ** 2)
+    diff = np.abs(dev.mean(axis=(0, 1)) - ref.mean(axis=(0, 1)))
+    assert np.all(diff <= 3 * sigma + 1e-7), (name, diff, sigma, diff / sigma)
+    psnr = helpers.psnr_after_gamma(dev, ref)
+    assert psnr >= 40.0, (name, psnr)
+
+
+@pytest.mark.parametrize("name,w,h", [("cornell", 96, 96), ("cornell_smoke", 96, 96)])
+def test_nee_has_the_same_mean_and_less_noise_than_plain_sampling(ctx, scene_of, name, w, h):
+    sc = scene_of(name)
+    ctx.upload(sc)
+    spp = 2048
+    pa, pb = _halves(ctx, w, h, spp, 50, nee=False)
+    na, nb = _halves(ctx, w, h, spp, 50, nee=True)
+    n = w * h
+    s_plain = 0.5 * np.sqrt(((pa - pb) ** 2).sum(axis=(0, 1))) / n
+    s_nee = 0.5 * np.sqrt(((na - nb) ** 2).sum(axis=(0, 1))) / n
+    diff = np.abs((0.5 * (pa + pb)).mean(axis=(0, 1)) - (0.5 * (na + nb)).mean(axis=(0, 1)))
+    assert np.all(diff <= 3 * np.sqrt(s_plain ** 2 + s_nee ** 2) + 1e-7), (diff, s_plain, s_nee)
+    # per-pixel noise: the two halves of the NEE render agree much better than the plain ones
+    noise_plain, noise_nee = np.mean((pa - pb) ** 2), np.mean((na - nb) ** 2)
+    assert noise_nee < 0.5 * noise_plain, (noise_plain, noise_nee)
+
+
+def test_nee_without_listed_emitters_is_the_plain_estimator(ctx, scene_of):
+    """book1 has no quad emitter: the flag changes nothing, bit for bit."""
+    ctx.upload(scene_of("book1"))
+    ctx.render(120, 68, 4, seed=3)
+    plain = ctx.accum_download()
+    ctx.render(120, 68, 4, seed=3, nee=True)
+    assert np.array_equal(plain, ctx.accum_download())
+
+
+def test_nee_is_deterministic_and_shardable(ctx, scene_of):
+    ctx.upload(scene_of("cornell"))
+    ctx.render(64, 64, 6, seed=5, nee=True)
+    whole = ctx.accum_download()
+    ctx.render(64, 64, 6, seed=5, nee=True, shard_rank=0, shard_count=2, shard_mode=2)
+    ctx.render(64, 64, 6, seed=5, nee=True, shard_rank=1, shard_count=2, shard_mode=2, accumulate=True)
+    assert np.array_equal(whole, ctx.accum_download())
