@@ -77,3 +77,33 @@ def test_nee_is_deterministic_and_shardable(ctx, scene_of):
     ctx.render(64, 64, 6, seed=5, nee=True, shard_rank=0, shard_count=2, shard_mode=2)
     ctx.render(64, 64, 6, seed=5, nee=True, shard_rank=1, shard_count=2, shard_mode=2, accumulate=True)
     assert np.array_equal(whole, ctx.accum_download())
+
+
+def test_camera_render_takes_the_flag(built, tmp_path):
+    """The reference-facing call: `cam.next_event_estimation = true; cam.render(world, lights)`
+    (apps/rtow_b200 --nee 1) writes the PNG of the same frame the C ABI renders with RT_FLAG_NEE."""
+    import os
+    import struct
+    import subprocess
+    import zlib
+
+    from raytracingoneweekendapplication_b200.assets import ensure_assets
+
+    exe = os.path.join(helpers.ROOT, "apps", "rtow_b200")
+    out = str(tmp_path / "cornell_nee.png")
+    r = subprocess.run([exe, "cornell", out, ensure_assets(), "72", "72", "6", "--nee", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    data = open(out, "rb").read()
+    w, h = struct.unpack(">II", data[16:24])
+    idat = data[data.index(b"IDAT") + 4: data.index(b"IEND") - 8]
+    png = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + 3 * w)[:, 1:].reshape(h, w, 3)
+    sc = capi.Scene("cornell")
+    c = capi.Context(0)
+    c.upload(sc)
+    c.render(72, 72, 6, max_depth=sc.depth, seed=1, nee=True)
+    with_nee = c.download(6, linear=False, rgb8=True)
+    c.render(72, 72, 6, max_depth=sc.depth, seed=1)
+    plain = c.download(6, linear=False, rgb8=True)
+    c.close()
+    assert np.array_equal(png, with_nee)
+    assert not np.array_equal(png, plain)
