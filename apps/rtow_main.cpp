@@ -40,6 +40,7 @@ int main(int argc, char** argv) {
         else if (k == "--stop-after") cam.stop_after_spp = std::atoi(argv[i + 1]);
         else if (k == "--linear") cam.linear_name = argv[i + 1];
         else if (k == "--nee") cam.next_event_estimation = std::atoi(argv[i + 1]) != 0;
+        else if (k == "--shadowed-point-lights") cam.shadowed_point_lights = std::atoi(argv[i + 1]) != 0;
         else { std::cerr << "unknown option " << k << std::endl; return 1; }
     }
     cam.image_name = out.c_str();

@@ -22,7 +22,7 @@ RT_PRIM_SPHERE, RT_PRIM_QUAD, RT_PRIM_TRIANGLE = range(3)
  RT_MAT_SPECULAR) = range(7)
 RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_CHECKER_TRIANGLE, RT_TEX_IMAGE, RT_TEX_NOISE = range(5)
 RT_SHARD_AUTO, RT_SHARD_TILES, RT_SHARD_SAMPLES = range(3)
-RT_FLAG_ACCUMULATE, RT_FLAG_ASYNC, RT_FLAG_STATS, RT_FLAG_NEE = 1, 2, 4, 8
+RT_FLAG_ACCUMULATE, RT_FLAG_ASYNC, RT_FLAG_STATS, RT_FLAG_NEE, RT_FLAG_SHADOWED_POINT_LIGHTS = 1, 2, 4, 8, 16
 
 d3 = C.c_double * 3
 
@@ -325,14 +325,14 @@ class Context:
     def render(self, width: int, height: int, spp: int, max_depth: int = 50, seed: int = 1, spp_begin: int = 0,
                accumulate: bool = False, stats: bool = False, shard_rank: int = 0, shard_count: int = 1,
                shard_mode: int = RT_SHARD_AUTO, tile_size: int = 0, stream: Optional[int] = None, blocking: bool = True,
-               nee: bool = False) -> None:
+               nee: bool = False, shadowed_point_lights: bool = False) -> None:
         p = rt_render_params()
         p.struct_size = C.sizeof(rt_render_params)
         p.width, p.height, p.samples_per_pixel, p.max_depth = width, height, spp, max_depth
         p.spp_begin, p.seed, p.tile_size = spp_begin, seed, tile_size
         p.shard_mode, p.shard_rank, p.shard_count = shard_mode, shard_rank, shard_count
         p.flags = ((RT_FLAG_ACCUMULATE if accumulate else 0) | (RT_FLAG_STATS if stats else 0) | (0 if blocking else RT_FLAG_ASYNC) |
-                   (RT_FLAG_NEE if nee else 0))
+                   (RT_FLAG_NEE if nee else 0) | (RT_FLAG_SHADOWED_POINT_LIGHTS if shadowed_point_lights else 0))
         p.stream = stream
         self._check(self.lib.rt_render(self._h, C.byref(p)))
         self.width, self.height = width, height

@@ -48,6 +48,8 @@ struct RenderArgs {
     int blocks_per_tile_x, blocks_per_tile_y;  // 8x4 pixel blocks per tile
     unsigned long long n_items;
     uint32_t k0, k1;
+    int nee_emitters;        // NEE instance: sample the listed quad emitters (RT_FLAG_NEE)
+    int shadow_point_lights; // NEE instance: shadow rays for the point lights (RT_FLAG_SHADOWED_POINT_LIGHTS)
 };
 
 constexpr float kAccumScale = 268435456.0f;  // 2^RT_ACCUM_FRAC_BITS
@@ -408,10 +410,13 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __g
                 if (!scattered) {
                     done = true;
                 } else {
-                    if (!LITE && S.n_lights > 0) L = L + T * att * point_lighting(S, sf.p, sf.normal);
+                    if (!LITE && S.n_lights > 0) {
+                        if (NEE && A.shadow_point_lights) L = L + T * att * point_lighting_shadowed(S, sf.p, sf.normal, origin_prim, ray.time, &counters[1]);
+                        else L = L + T * att * point_lighting(S, sf.p, sf.normal);
+                    }
                     if (NEE) {
                         nee_pdf = 0.0f;
-                        if (S.n_nee_lights > 0 && (m.type == RT_MAT_LAMBERTIAN || m.type == RT_MAT_ISOTROPIC)) {
+                        if (A.nee_emitters && S.n_nee_lights > 0 && (m.type == RT_MAT_LAMBERTIAN || m.type == RT_MAT_ISOTROPIC)) {
                             const bool iso = m.type == RT_MAT_ISOTROPIC;
                             nee_pdf = scatter_density(normalize(next.d), sf.normal, iso);
                             L = L + T * att * nee_direct(S, sf.p, sf.normal, iso, origin_prim, ray.time, rng.draw(bounce, RS_NEE), &counters[1]);
@@ -1477,7 +1482,9 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
                 cudaFuncSetAttribute(render_kernel_v2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
                 cudaFuncSetAttribute(render_kernel_v2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             }
-            const bool nee = (p->flags & RT_FLAG_NEE) != 0 && ctx->scene.n_nee_lights > 0;
+            A.nee_emitters = (p->flags & RT_FLAG_NEE) != 0 && ctx->scene.n_nee_lights > 0;
+            A.shadow_point_lights = (p->flags & RT_FLAG_SHADOWED_POINT_LIGHTS) != 0 && ctx->scene.n_lights > 0;
+            const bool nee = A.nee_emitters || A.shadow_point_lights;
             if (nee && lite) render_kernel_v2<false, true, true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
             else if (nee) render_kernel_v2<false, false, true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
             else if (stats) render_kernel_v2<true, false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);

@@ -919,6 +919,41 @@ __device__ __noinline__ V3 nee_direct(const DevScene& S, V3 p, V3 n, bool isotro
     return weight * tex_value(S, lt.tex, u.y, u.z, y);
 }
 
+// Camera.txt:240-272 with the one thing the reference leaves out: a shadow ray per light
+// (RT_FLAG_SHADOWED_POINT_LIGHTS, opt-in -- it changes the image on purpose: the reference's
+// point lights shine through everything).  Media on the way attenuate the light as well.
+__device__ __noinline__ V3 point_lighting_shadowed(const DevScene& S, V3 p, V3 normal, uint32_t origin_prim, float time,
+                                                   unsigned long long* overflow_flag) {
+    V3 result = v3(0, 0, 0);
+    for (int i = 0; i < S.n_lights; i++) {
+        const DevLight& l = S.lights[i];
+        V3 ld = v3(l.pos) - p;
+        const float d2 = dot(ld, ld);
+        ld = (1.0f / sqrtf(d2)) * ld;
+        const float diffuse = fmaxf(dot(normal, ld), 0.0f);
+        if (!(diffuse > 0.0f)) continue;
+        const float dist = sqrtf(d2);
+        Ray sray;
+        sray.o = p;
+        sray.d = ld;
+        sray.time = time;
+        Hit h;
+        int ov = 0;
+        traverse<false>(S, sray, 0.001f, dist, origin_prim, h, nullptr, &ov);
+        if (ov) atomicAdd(overflow_flag, 1ull);
+        if (h.prim != PRIM_NONE) continue;
+        const float tm = S.n_media > 0 ? media_transmittance(S, sray, 0.001f, dist) : 1.0f;
+        // the same arithmetic as point_lighting, so that an unoccluded light gives the same bits
+        if (d2 <= l.size * l.size) {
+            result = result + (tm * diffuse) * v3(l.intensity);
+        } else {
+            float att = 1.0f / (d2 + l.size * 0.1f);
+            result = result + (tm * (diffuse * att)) * v3(l.intensity);
+        }
+    }
+    return result;
+}
+
 // Camera.txt:177-200 get_ray.  Directions are built relative to the camera centre
 // (dir00 = pixel00_loc - center, evaluated in double on the host) so that FP32 keeps
 // sub-pixel accuracy when the camera sits hundreds of units from the origin.

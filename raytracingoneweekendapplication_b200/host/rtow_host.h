@@ -1548,6 +1548,9 @@ class camera {
     //   next_event_estimation  opt-in: sample the quad emitters directly at diffuse
     //                    and isotropic vertices (RT_FLAG_NEE); same converged image, far less noise
     bool next_event_estimation = false;
+    //   shadowed_point_lights  opt-in: shadow rays for the point lights (RT_FLAG_SHADOWED_POINT_LIGHTS);
+    //                    the reference's are unshadowed (Camera.txt:240-272), so this changes the image
+    bool shadowed_point_lights = false;
     std::string linear_name;
     std::string checkpoint_path;
     int checkpoint_every_spp = 0;
@@ -1633,7 +1636,8 @@ class camera {
             if (!checkpoint_path.empty() && checkpoint_every_spp > 0) n = std::min(n, std::max(1, checkpoint_every_spp - since_save));
             p.samples_per_pixel = n;
             p.spp_begin = done;
-            p.flags = (fresh ? 0 : RT_FLAG_ACCUMULATE) | (next_event_estimation ? RT_FLAG_NEE : 0);
+            p.flags = (fresh ? 0 : RT_FLAG_ACCUMULATE) | (next_event_estimation ? RT_FLAG_NEE : 0) |
+                      (shadowed_point_lights ? RT_FLAG_SHADOWED_POINT_LIGHTS : 0);
             fresh = false;
             if (rt_render(ctx, &p) != RT_OK) fail("rt_render");
             done += n;

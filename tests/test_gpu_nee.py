@@ -107,3 +107,53 @@ def test_camera_render_takes_the_flag(built, tmp_path):
     c.close()
     assert np.array_equal(png, with_nee)
     assert not np.array_equal(png, plain)
+
+
+def test_shadowed_point_lights(built):
+    """RT_FLAG_SHADOWED_POINT_LIGHTS: a floor, a sphere above it, a point light above the sphere and a
+    black sky.  The reference's unshadowed term (Camera.txt:240-272) lights the floor under the
+    sphere as if the sphere were not there; with the flag that patch goes dark and nothing else changes."""
+    import ctypes as C
+
+    import fuzz_scenes
+
+    d3 = fuzz_scenes.d3
+    tex = capi.rt_texture()
+    tex.type, tex.even, tex.odd, tex.image, tex.perlin = capi.RT_TEX_SOLID, -1, -1, -1, -1
+    tex.color = d3((0.8, 0.8, 0.8))
+    mat = capi.rt_material()
+    mat.type, mat.texture = capi.RT_MAT_LAMBERTIAN, 0
+    floor = capi.rt_quad()
+    floor.Q, floor.u, floor.v = d3((-20, 0, -20)), d3((40, 0, 0)), d3((0, 0, 40))
+    floor.material, floor.xform = 0, -1
+    ball = capi.rt_sphere()
+    ball.center0, ball.center_vec, ball.radius = d3((0, 3, 0)), d3((0, 0, 0)), 1.5
+    ball.material, ball.xform = 0, -1
+    light = capi.rt_point_light()
+    light.position, light.intensity, light.size = d3((0, 6, 0)), d3((40, 40, 40)), 0.1
+    cam = capi.rt_camera()
+    cam.lookfrom, cam.lookat, cam.vup = d3((0, 14, 0.01)), d3((0, 0, 0)), d3((0, 0, -1))
+    cam.vfov, cam.defocus_angle, cam.focus_dist = 60, 0, 10
+    cam.background = d3((0, 0, 0))
+    sc = fuzz_scenes.PyScene([ball], [floor], [], [], [mat], [tex], camera=cam, lights=[light])
+    c = capi.Context(0)
+    c.upload(sc)
+    w = h = 96
+    c.render(w, h, 64, max_depth=1, seed=1)                       # depth 1: the point-light term of the first hit only
+    plain = c.download(64).mean(axis=2)
+    c.render(w, h, 64, max_depth=1, seed=1, shadowed_point_lights=True)
+    shadowed = c.download(64).mean(axis=2)
+    aov = c.aov(w, h)["prim_id"].reshape(h, w)
+    c.close()
+    floor_px = aov == [r.type for r in sc.desc.world[:2]].index(1)   # the quad's canonical id
+    # the shadow is a disc of radius 1.5 * 6 / sqrt(3^2 - 1.5^2) = 3.46 (20 pixels) around the centre, the ball's
+    # silhouette covers 11 pixels of it: the ring of floor between 13 and 18 pixels is in shadow
+    yy, xx = np.mgrid[0:h, 0:w]
+    r_px = np.hypot(xx - (w - 1) / 2, yy - (h - 1) / 2)
+    ring = floor_px & (r_px > 13) & (r_px < 18)
+    assert ring.sum() > 100
+    assert plain[ring].min() > 0.05 and shadowed[ring].max() < 1e-6
+    far = floor_px & (r_px > 40)
+    assert np.array_equal(plain[far], shadowed[far])
+    ball_px = ~floor_px & (r_px < 9)                                 # well inside the silhouette (samples are jittered)
+    assert ball_px.sum() > 100 and np.array_equal(plain[ball_px], shadowed[ball_px])   # the ball itself is lit in both
