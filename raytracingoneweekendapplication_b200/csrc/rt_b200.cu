@@ -944,6 +944,7 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
         if (const char* e = getenv("RT_B200_MAX_LEAF")) tune.max_leaf = std::max(1, std::min(8, atoi(e)));
         if (const char* e = getenv("RT_B200_TRAV_COST")) tune.trav_cost = (float)atof(e);
         if (const char* e = getenv("RT_B200_SHORTCUT_MIN")) tune.shortcut_min = (size_t)atoll(e);
+        if (const char* e = getenv("RT_B200_ALL_AXES")) tune.all_axes_max = (uint32_t)atoll(e);
         rtbvh::build_bvh(prims, bvh, tune);
     }
     const size_t first_boundary = device_build ? 0 : (size_t)sc->n_world;
