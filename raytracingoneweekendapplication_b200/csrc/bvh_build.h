@@ -55,7 +55,10 @@ struct Result {
     uint32_t depth = 0, leaves = 0;
 };
 
-constexpr int kBins = 16;
+#ifndef RT_SAH_BINS
+#define RT_SAH_BINS 16
+#endif
+constexpr int kBins = RT_SAH_BINS;
 constexpr int kAllAxes = 8192;
 struct Tuning {
     int max_leaf = 4;       // primitives per leaf (<= 8, the link encoding has 3 count bits)
