@@ -218,7 +218,7 @@ typedef enum rt_shard_mode {
                                  emitters of the scene directly (shadow ray, media transmittance), weighted with the
                                  density of the reference's own direction sampler, so the CONVERGED image is the one
                                  the reference converges to; individual samples differ, noise is lower.  Ignored when
-                                 the scene has no quad emitter or was uploaded by the device builder. */
+                                 the scene has no quad emitter. */
 #define RT_FLAG_SHADOWED_POINT_LIGHTS 16u /* opt-in: a shadow ray (and media transmittance) per point light in the
                                  term of Camera.txt:240-272.  The reference's point lights are unshadowed, so this
                                  changes the image on purpose. */

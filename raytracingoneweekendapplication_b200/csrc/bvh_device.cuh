@@ -65,6 +65,7 @@ struct Scratch {
     uint32_t *val_in, *val_out;            // primitive index
     uint32_t *flag, *scan, *rank_at;       // per sorted position
     float* cost;                           // per internal node: SAH cost of its best completion
+    const int* quad_light;                 // per SOURCE quad: its number in the next-event emitter list (0: none); may be null
     int *left, *right, *parent_int, *parent_leaf, *range_first;
     float4 *nbox_lo, *nbox_hi;             // per internal node; lo.w = count bits, hi.w = type mask | height << 8
     unsigned* visit;
@@ -353,7 +354,9 @@ __global__ void __launch_bounds__(256) prims_kernel(Scratch W, Targets T) {
         const rtprep::QuadRec v = rtprep::make_quad(b);
         for (int q = 0; q < 3; q++) T.quad[3 * r + q] = f4(v.q[q]);
         for (int q = 0; q < 12; q++) T.quad_d[12 * r + q] = v.d[q];
-        T.quad_sh[r] = i4(v.sh);
+        int4 sh = i4(v.sh);
+        if (W.quad_light) sh.w = W.quad_light[W.world[s].index];
+        T.quad_sh[r] = sh;
     } else if (b.dev_type == rtprep::PREP_SPHERE) {
         const rtprep::SphereRec v = rtprep::make_sphere(b);
         T.sph[r] = f4(v.g);
@@ -383,7 +386,7 @@ struct ScratchPlan {
 struct Layout {
     size_t world, spheres, quads, triangles, xforms;
     size_t box_lo, box_hi, key_in, key_out, val_in, val_out, flag, scan, rank_at, left, right, parent_int, parent_leaf, range_first,
-        nbox_lo, nbox_hi, visit, bounds, counters, cub_temp, clusters, cost;
+        nbox_lo, nbox_hi, visit, bounds, counters, cub_temp, clusters, cost, quad_light;
     size_t cub_temp_bytes, total;
 };
 
@@ -411,6 +414,7 @@ inline Layout plan_scratch(const rt_scene_desc* sc) {
     L.cub_temp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
     L.cub_temp = p.add(L.cub_temp_bytes);
     L.clusters = p.add((size_t)kMaxClusters * sizeof(Cluster));
+    L.quad_light = p.add((size_t)sc->n_quads * sizeof(int));
     L.total = p.size;
     return L;
 }
@@ -487,7 +491,8 @@ struct BuildResult {
 // Copies the raw arrays of `sc` into `scratch` and runs the build on `stream`.  `T` points into
 // the scene arena.  Returns a cudaError_t-compatible code (0 = success).
 inline cudaError_t build_on_device(const rt_scene_desc* sc, unsigned char* scratch, const Layout& L, const Targets& T,
-                                   cudaStream_t stream, CopyRing& ring, int device, bool hybrid_top, BuildResult& out) {
+                                   cudaStream_t stream, CopyRing& ring, int device, bool hybrid_top, const int* quad_light,
+                                   BuildResult& out) {
     const int n = sc->n_world;
     Scratch W{};
     auto at = [&](size_t off) { return scratch + off; };
@@ -502,6 +507,7 @@ inline cudaError_t build_on_device(const rt_scene_desc* sc, unsigned char* scrat
     RT_COPY_IN(quads, sc->quads, sc->n_quads, rt_quad)
     RT_COPY_IN(triangles, sc->triangles, sc->n_triangles, rt_triangle)
     RT_COPY_IN(xforms, sc->xforms, sc->n_xforms, rt_xform)
+    if (quad_light) { RT_COPY_IN(quad_light, quad_light, sc->n_quads, int) }
 #undef RT_COPY_IN
     cudaEventRecord(ev[1], stream);
     W.world = (const rt_prim_ref*)at(L.world);
@@ -513,6 +519,7 @@ inline cudaError_t build_on_device(const rt_scene_desc* sc, unsigned char* scrat
     W.val_in = (uint32_t*)at(L.val_in); W.val_out = (uint32_t*)at(L.val_out);
     W.flag = (uint32_t*)at(L.flag); W.scan = (uint32_t*)at(L.scan); W.rank_at = (uint32_t*)at(L.rank_at);
     W.cost = (float*)at(L.cost);
+    W.quad_light = quad_light ? (const int*)at(L.quad_light) : nullptr;
     W.left = (int*)at(L.left); W.right = (int*)at(L.right); W.parent_int = (int*)at(L.parent_int);
     W.parent_leaf = (int*)at(L.parent_leaf); W.range_first = (int*)at(L.range_first);
     W.nbox_lo = (float4*)at(L.nbox_lo); W.nbox_hi = (float4*)at(L.nbox_hi);

@@ -984,7 +984,7 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
             return (PT_TRI << 28) | (uint32_t)(world_count[PT_TRI] + tri_sh.size() / 3 - 1);
         }
     };
-    // quads with an emissive material are also listed for the opt-in next-event estimation (host path only)
+    // quads with an emissive material are also listed for the opt-in next-event estimation
     std::vector<DevNeeLight> nee_lights;
     double nee_area = 0.0;
     for (uint32_t id : bvh.order) {
@@ -1008,6 +1008,34 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
         lt.cdf = (float)nee_area;  // normalised below
         nee_lights.push_back(lt);
         quad_sh[(packed & 0x0fffffffu) - world_count[PT_QUAD]].w = (int)nee_lights.size();
+    }
+    // device path: the emitters are found in the source array (one pass over the quads, not over the
+    // world list); the kernels that write the quad records look the light number up by source index
+    std::vector<int32_t> quad_light;
+    if (device_build) {
+        for (int i = 0; i < sc->n_quads; i++) {
+            const rt_quad& q = sc->quads[i];
+            if (q.material < 0 || q.material >= sc->n_materials) continue;
+            const rt_material& m = sc->materials[q.material];
+            if (m.type != RT_MAT_DIFFUSE_LIGHT && m.type != RT_MAT_EMISSIVE_LIGHT) continue;
+            const BakedPrim b = rtprep::bake_prim(src, rt_prim_ref{RT_PRIM_QUAD, i}, -1);
+            const D3 nn = dcross(b.b, b.c);
+            const double area = std::sqrt(ddot(nn, nn));
+            if (!(area > 0.0)) continue;
+            DevNeeLight lt;
+            std::memset(&lt, 0, sizeof lt);
+            lt.Q[0] = (float)b.a.x; lt.Q[1] = (float)b.a.y; lt.Q[2] = (float)b.a.z;
+            lt.u[0] = (float)b.b.x; lt.u[1] = (float)b.b.y; lt.u[2] = (float)b.b.z;
+            lt.v[0] = (float)b.c.x; lt.v[1] = (float)b.c.y; lt.v[2] = (float)b.c.z;
+            lt.n[0] = (float)(nn.x / area); lt.n[1] = (float)(nn.y / area); lt.n[2] = (float)(nn.z / area);
+            lt.area = (float)area;
+            lt.tex = m.texture;
+            nee_area += area;
+            lt.cdf = (float)nee_area;
+            nee_lights.push_back(lt);
+            if (quad_light.empty()) quad_light.assign((size_t)sc->n_quads, 0);
+            quad_light[(size_t)i] = (int32_t)nee_lights.size();
+        }
     }
     for (DevNeeLight& lt : nee_lights) lt.cdf = (float)(lt.cdf / nee_area);
     if (!nee_lights.empty()) nee_lights.back().cdf = 1.0f;
@@ -1170,7 +1198,8 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
         if ((size_t)sc->n_triangles * sizeof(rt_triangle) >= 4 * rtlbvh::kCopyChunk || (size_t)sc->n_quads * sizeof(rt_quad) >= 4 * rtlbvh::kCopyChunk ||
             (size_t)sc->n_spheres * sizeof(rt_sphere) >= 4 * rtlbvh::kCopyChunk)
             CU(ctx, ctx->copy_ring.init());
-        CU(ctx, rtlbvh::build_on_device(sc, ctx->scratch, L, T, ctx->stream, ctx->copy_ring, ctx->device, ctx->bvh_builder != 3, br));
+        CU(ctx, rtlbvh::build_on_device(sc, ctx->scratch, L, T, ctx->stream, ctx->copy_ring, ctx->device, ctx->bvh_builder != 3,
+                                        quad_light.empty() ? nullptr : quad_light.data(), br));
         n_nodes = br.nodes;
         depth = br.depth;
         leaves = br.leaves;

@@ -157,3 +157,22 @@ def test_shadowed_point_lights(built):
     assert np.array_equal(plain[far], shadowed[far])
     ball_px = ~floor_px & (r_px < 9)                                 # well inside the silhouette (samples are jittered)
     assert ball_px.sum() > 100 and np.array_equal(plain[ball_px], shadowed[ball_px])   # the ball itself is lit in both
+
+
+def test_nee_is_the_same_with_the_device_built_scene(scene_of):
+    """The device upload path builds the emitter list from the source quad array; same records, same
+    light numbers, so an NEE frame does not depend on who built the scene."""
+    sc = scene_of("final")
+    frames = []
+    for mode in ("host", "device"):
+        c = capi.Context(0)
+        c.set_bvh_builder(mode)
+        c.upload(sc)
+        c.render(160, 90, 4, max_depth=50, seed=6, nee=True)
+        frames.append(c.accum_download())
+        c.render(160, 90, 4, max_depth=50, seed=6)
+        frames.append(c.accum_download())
+        c.close()
+    assert np.array_equal(frames[0], frames[2])
+    assert np.array_equal(frames[1], frames[3])
+    assert not np.array_equal(frames[0], frames[1])
