@@ -48,7 +48,7 @@ typedef enum rt_status {
     RT_ERR_NOMEM = 3,       /* host or device allocation failed              */
     RT_ERR_STATE = 4,       /* call order violated (e.g. render before upload) */
     RT_ERR_UNSUPPORTED = 5, /* feature outside the hot path                  */
-    RT_ERR_KERNEL = 6       /* device-side guard tripped (traversal stack overflow) */
+    RT_ERR_KERNEL = 6       /* device-side guard tripped (reserved: the traversal stack depth is checked at upload) */
 } rt_status;
 
 /* ---------------------------------------------------------------------------

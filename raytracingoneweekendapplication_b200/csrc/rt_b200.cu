@@ -1169,6 +1169,9 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
         if (b.bytes) std::memcpy(ctx->staging + (device_build ? b.stage_off : b.off), b.src, b.bytes);
         *b.field = ctx->arena + b.off;
     }
+    // the traversal stack is not bounds-checked on the device (rt_device.cuh, Trav::interior)
+    if (!device_build && bvh.depth >= (uint32_t)STACK_SIZE)
+        return fail(ctx, RT_ERR_UNSUPPORTED, "rt_upload_scene: the BVH has %u levels, the traversal stack holds %d", bvh.depth, STACK_SIZE);
     uint32_t n_nodes = (uint32_t)bvh.nodes.size(), depth = bvh.depth, leaves = bvh.leaves;
     int root = bvh.root, device_nodes = 0;
     if (!device_build) {

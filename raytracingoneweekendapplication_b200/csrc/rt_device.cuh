@@ -25,7 +25,7 @@ namespace rtdev {
 
 enum : uint32_t { PT_SPHERE = 0, PT_MSPHERE = 1, PT_QUAD = 2, PT_TRI = 3 };
 constexpr uint32_t PRIM_NONE = 0xffffffffu;
-constexpr int STACK_SIZE = 64;  // power of two (the index is masked); BVH2 depth of a SAH tree over 2^25 prims stays below
+constexpr int STACK_SIZE = 64;  // levels a tree may have (checked at upload); BVH2 depth of a SAH tree over 2^25 prims stays below
 
 struct DevMaterial {  // 32 B
     int type;
@@ -401,8 +401,10 @@ struct Trav {
         const int far_l = right_first ? linkl : linkr;
         const float far_t = right_first ? ln : rn;
         if (hl && hr) {
-            stack[sp & (STACK_SIZE - 1)] = pack_entry(far_l, far_t);
-            if (sp >= STACK_SIZE) *overflow = 1;
+            // no bounds check here: a ray's stack never holds more entries than the tree has levels, and
+            // rt_upload_scene refuses (host path) or rebuilds on the host (device path) a tree with
+            // STACK_SIZE levels or more.  The masked index + overflow flag this replaces cost 2.5 % on C5.
+            stack[sp] = pack_entry(far_l, far_t);
             sp++;
         }
         if (hl || hr) cur = near_l;
