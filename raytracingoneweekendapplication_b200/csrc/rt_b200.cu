@@ -216,6 +216,9 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Dev
 #ifndef RT_MIN_BLOCKS
 #define RT_MIN_BLOCKS 3
 #endif
+#ifndef RT_V2_THREADS
+#define RT_V2_THREADS 256  // threads per block of render_kernel_v2 (tuning experiments: 224 x 3 trades warps for registers)
+#endif
 #ifndef RT_DESCEND_DIV
 #define RT_DESCEND_DIV 0
 #endif
@@ -228,7 +231,7 @@ constexpr int kDescendDiv = RT_DESCEND_DIV;
 enum : int { LANE_IDLE = 0, LANE_TRAVERSE = 1, LANE_SHADE = 2 };
 
 template <bool STATS, bool LITE, bool NEE = false>
-__global__ void __launch_bounds__(256, RT_MIN_BLOCKS) render_kernel_v2(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A,
+__global__ void __launch_bounds__(RT_V2_THREADS, RT_MIN_BLOCKS) render_kernel_v2(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A,
                                                         unsigned long long* __restrict__ accum,
                                                         unsigned long long* __restrict__ counters, Stats* __restrict__ gstats) {
     const unsigned lane = threadIdx.x & 31u;
@@ -740,13 +743,13 @@ extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
         CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], render_kernel_v3<true, false>, 256, 0));
         CU(ctx, cudaFuncGetAttributes(&fa, render_kernel_v3<false, false>));
     } else {
-        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], render_kernel_v2<false, false>, 256, 0));
-        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], render_kernel_v2<true, false>, 256, 0));
+        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], render_kernel_v2<false, false>, RT_V2_THREADS, 0));
+        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], render_kernel_v2<true, false>, RT_V2_THREADS, 0));
         CU(ctx, cudaFuncGetAttributes(&fa, render_kernel_v2<false, false>));
     }
     ctx->stats.regs_per_thread = fa.numRegs;
     ctx->stats.local_bytes_per_thread = (uint32_t)fa.localSizeBytes;
-    ctx->stats.threads_per_block = 256;
+    ctx->stats.threads_per_block = ctx->kernel_version == 2 ? RT_V2_THREADS : 256;
     return RT_OK;
 }
 
@@ -1475,7 +1478,7 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
     // segment length: enough work items to keep every resident warp busy ~64 times over,
     // but never shorter than 1 sample (fixed-point sums make the split result-neutral)
     const unsigned long long pixel_blocks = (unsigned long long)A.n_local_tiles * A.blocks_per_tile_x * A.blocks_per_tile_y;
-    const unsigned long long resident_warps = (unsigned long long)grid * 8ull;
+    const unsigned long long resident_warps = (unsigned long long)grid * (ctx->kernel_version == 2 ? RT_V2_THREADS / 32 : 8);
     int n_seg = 1;
     if (A.n_local_samples > 0 && pixel_blocks > 0) {
         // >= 64 items per resident warp: the end-of-kernel tail is one item long
@@ -1523,11 +1526,11 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
             A.nee_emitters = (p->flags & RT_FLAG_NEE) != 0 && ctx->scene.n_nee_lights > 0;
             A.shadow_point_lights = (p->flags & RT_FLAG_SHADOWED_POINT_LIGHTS) != 0 && ctx->scene.n_lights > 0;
             const bool nee = A.nee_emitters || A.shadow_point_lights;
-            if (nee && lite) render_kernel_v2<false, true, true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
-            else if (nee) render_kernel_v2<false, false, true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
-            else if (stats) render_kernel_v2<true, false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
-            else if (lite) render_kernel_v2<false, true><<<grid, 256, dummy, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
-            else render_kernel_v2<false, false><<<grid, 256, dummy, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            if (nee && lite) render_kernel_v2<false, true, true><<<grid, RT_V2_THREADS, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            else if (nee) render_kernel_v2<false, false, true><<<grid, RT_V2_THREADS, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            else if (stats) render_kernel_v2<true, false><<<grid, RT_V2_THREADS, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            else if (lite) render_kernel_v2<false, true><<<grid, RT_V2_THREADS, dummy, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            else render_kernel_v2<false, false><<<grid, RT_V2_THREADS, dummy, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
         }
         CU(ctx, cudaGetLastError());
         if (ctx->kernel_version != 3) ctx->stats.kernel_launches = 1;
