@@ -330,10 +330,12 @@ __device__ __forceinline__ void hit_prim(const DevScene& S, uint32_t type, uint3
 struct RayConst {  // per-ray constants of the slab test, recomputed when a traversal phase starts
     float idx, idy, idz, ox, oy, oz, inv_a;
     __device__ __forceinline__ void set(const Ray& ray) {
-        auto safe_inv = [](float d) { return 1.0f / (fabsf(d) > 1e-30f ? d : copysignf(1e-30f, d)); };
+        // __frcp_rn: the correctly rounded reciprocal (same value as 1.0f / x) without the generic
+        // division's slow path -- this runs for every lane at the start of every traversal phase
+        auto safe_inv = [](float d) { return __frcp_rn(fabsf(d) > 1e-30f ? d : copysignf(1e-30f, d)); };
         idx = safe_inv(ray.d.x); idy = safe_inv(ray.d.y); idz = safe_inv(ray.d.z);
         ox = ray.o.x * idx; oy = ray.o.y * idy; oz = ray.o.z * idz;
-        inv_a = 1.0f / dot(ray.d, ray.d);
+        inv_a = __frcp_rn(dot(ray.d, ray.d));
     }
 };
 
@@ -712,7 +714,7 @@ __device__ __forceinline__ void complete_hit(const DevScene& S, const Ray& ray, 
 __device__ __forceinline__ V3 random_unit_vector(float ux, float uy, float uz) {
     V3 p = v3(fmaf(2.0f, ux, -1.0f), fmaf(2.0f, uy, -1.0f), fmaf(2.0f, uz, -1.0f));
     float lensq = dot(p, p);
-    return (1.0f / sqrtf(lensq)) * p;
+    return rsqrtf(lensq) * p;
 }
 __device__ __forceinline__ V3 reflect(V3 v, V3 n) { return v - 2.0f * dot(v, n) * n; }
 __device__ __forceinline__ bool near_zero(V3 v) { return fabsf(v.x) < 1e-8f && fabsf(v.y) < 1e-8f && fabsf(v.z) < 1e-8f; }
