@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 2
+#define RT_B200_ABI_VERSION 3
 
 typedef struct rt_ctx rt_ctx;
 
@@ -275,6 +275,10 @@ typedef struct rt_stats {
     uint32_t bvh_on_device, reserved_;
     double device_build_ms, device_copy_in_ms;
     double device_top_ms; /* host time of the SAH top levels of the device-built tree (sync + copies included) */
+    /* acceleration structure the render kernels traverse: 2 = binary tree of 64-byte nodes, 8 / 4 = wide
+     * tree with 8-bit quantised child boxes (80 / 48 bytes per node); node count and levels of the wide tree */
+    uint32_t bvh_width, wide_nodes, wide_depth, reserved2_;
+    uint64_t empty_node_steps; /* node steps in which no child box was hit (RT_FLAG_STATS) */
 } rt_stats;
 
 /* Create a context on CUDA device `device_ids[0]` (n_devices must be 1: this
@@ -300,6 +304,14 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene);
  * Images do not depend on the choice (same records bit for bit, closest hit is tree-independent)
  * except where two primitives are hit at exactly the same t. */
 int rt_set_bvh_builder(rt_ctx* ctx, int32_t mode);
+
+/* Which acceleration structure the next rt_upload_scene builds for the render kernels (replaces
+ * bvh.h:64-72 + aabb.h:61-85 either way): 2 = the SAH binary tree (64-byte nodes, two child boxes
+ * each); 8 or 4 = the same tree collapsed into a wide BVH with 8-bit quantised child boxes and
+ * octant-ordered child slots (csrc/bvh_wide.h).  Closest hits, and therefore images, do not depend on
+ * the choice except where two primitives are hit at exactly the same t.  Scenes built by the device
+ * builder keep the binary tree.  Environment RT_B200_BVH_WIDTH=2|4|8 sets the default at rt_create. */
+int rt_set_bvh_width(rt_ctx* ctx, int32_t width);
 
 /* Runs the whole bounce loop (Camera.txt:65-93, 177-272) for this context's
  * shard of samples [spp_begin, spp_begin + samples_per_pixel) and adds the

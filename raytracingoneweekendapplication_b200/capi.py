@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-RT_B200_ABI_VERSION = 2
+RT_B200_ABI_VERSION = 3
 RT_ACCUM_FRAC_BITS = 28
 
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_NOMEM, RT_ERR_STATE, RT_ERR_UNSUPPORTED, RT_ERR_KERNEL = range(7)
@@ -121,6 +121,8 @@ class rt_stats(C.Structure):
         ("trav_hist", C.c_uint64 * 208),
         ("bvh_on_device", C.c_uint32), ("reserved_", C.c_uint32), ("device_build_ms", C.c_double), ("device_copy_in_ms", C.c_double),
         ("device_top_ms", C.c_double),
+        ("bvh_width", C.c_uint32), ("wide_nodes", C.c_uint32), ("wide_depth", C.c_uint32), ("reserved2_", C.c_uint32),
+        ("empty_node_steps", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:
@@ -131,6 +133,7 @@ EXPORTED_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_upload_scene", "rt_render", "rt_sync", "rt_download", "rt_render_aov",
     "rt_accum_buffer", "rt_bind_accum", "rt_get_stats", "rt_measure_fp32_peak", "rt_probe_texture", "rt_probe_scatter",
     "rt_probe_hit", "rt_struct_size", "rt_accum_download", "rt_accum_upload", "rt_set_bvh_builder",
+    "rt_set_bvh_width",
 ]
 
 ABI_STRUCTS = [rt_scene_desc, rt_render_params, rt_stats, rt_sphere, rt_quad, rt_triangle, rt_medium, rt_material, rt_texture,
@@ -180,6 +183,7 @@ def load() -> C.CDLL:
     lib.rt_bind_accum.argtypes = [vp, vp, C.c_size_t, i32, i32]
     lib.rt_get_stats.argtypes = [vp, C.POINTER(rt_stats)]
     lib.rt_set_bvh_builder.argtypes = [vp, i32]
+    lib.rt_set_bvh_width.argtypes = [vp, i32]
     lib.rt_accum_download.argtypes = [vp, vp, C.c_size_t]
     lib.rt_accum_upload.argtypes = [vp, vp, C.c_size_t, i32, i32]
     lib.rt_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
@@ -312,6 +316,10 @@ class Context:
         """'auto' | 'host' (binned SAH on the CPU) | 'device' (LBVH in CUDA kernels + SAH top levels) |
         'lbvh' (device, pure LBVH) for the next upload."""
         self._check(self.lib.rt_set_bvh_builder(self._h, {"auto": 0, "host": 1, "device": 2, "lbvh": 3}[mode]))
+
+    def set_bvh_width(self, width: int) -> None:
+        """2 (binary tree) | 4 | 8 (wide quantised tree) for the next upload."""
+        self._check(self.lib.rt_set_bvh_width(self._h, width))
 
     def upload(self, scene) -> None:
         if hasattr(scene, "desc_ptr"):          # capi.Scene or any object that keeps a description alive

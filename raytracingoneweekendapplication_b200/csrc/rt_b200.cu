@@ -23,11 +23,19 @@
 #include <vector>
 
 #include "bvh_build.h"
+#include "bvh_wide.h"
 #include "prim_derive.h"
 #include "bvh_device.cuh"
 #include "rt_b200.h"
 #include "rt_device.cuh"
+#include "rt_wide.cuh"
+#ifdef RT_B200_ALT_KERNELS
+// The measured alternatives to render_kernel_v2: the first megakernel (v1), the
+// two-contexts-per-lane kernel (v3) and the wavefront pipeline.  All three lose to v2 on every
+// BASELINE scene; they are compiled only with -DRT_B200_ALT_KERNELS (build.py --alt) and selected
+// with RT_B200_KERNEL=v1|v3|wf.
 #include "rt_wavefront.cuh"
+#endif
 
 using namespace rtdev;
 
@@ -55,141 +63,9 @@ struct RenderArgs {
 constexpr float kAccumScale = 268435456.0f;  // 2^RT_ACCUM_FRAC_BITS
 constexpr float kSampleClamp = 1048576.0f;   // 2^20: keeps 2^16 saturated samples inside 64 bits
 
-template <bool STATS>
-__global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A,
-                                                     unsigned long long* __restrict__ accum,
-                                                     unsigned long long* __restrict__ counters, Stats* __restrict__ gstats) {
-    const unsigned lane = threadIdx.x & 31u;
-    Stats st;
-    if (STATS) memset(&st, 0, sizeof st);
-    int overflow = 0;
-    unsigned long long dropped = 0;
-
-    while (true) {
-        // one work item per warp: an 8x4 pixel block x one segment of samples
-        unsigned long long item = 0;
-        if (lane == 0) item = atomicAdd(&counters[0], 1ull);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= A.n_items) break;
-
-        const unsigned seg = (unsigned)(item % (unsigned long long)A.n_segments);
-        unsigned long long blk = item / (unsigned long long)A.n_segments;
-        const unsigned blocks_per_tile = (unsigned)(A.blocks_per_tile_x * A.blocks_per_tile_y);
-        const unsigned local_tile = (unsigned)(blk / blocks_per_tile);
-        const unsigned in_tile = (unsigned)(blk % blocks_per_tile);
-        const unsigned tile = A.tile_offset + local_tile * A.tile_stride;
-        const int tx = tile % A.tiles_x, ty = tile / A.tiles_x;
-        const int bx = in_tile % A.blocks_per_tile_x, by = in_tile / A.blocks_per_tile_x;
-        const int px = tx * A.tile_size + bx * 8 + (int)(lane & 7u);
-        const int py = ty * A.tile_size + by * 4 + (int)(lane >> 3);
-        const bool inside = px < A.width && py < A.height && (bx * 8 + (int)(lane & 7u)) < A.tile_size &&
-                            (by * 4 + (int)(lane >> 3)) < A.tile_size;
-        const uint32_t pixel = (uint32_t)(py * A.width + px);
-
-        int s = (int)seg * A.seg_len;
-        // ray_color(depth <= 0) is black before anything is traced (Camera.txt:205-206)
-        const int s_end = (inside && A.max_depth > 0) ? min(s + A.seg_len, A.n_local_samples) : s;
-
-        unsigned long long sum_r = 0, sum_g = 0, sum_b = 0;
-        Rng rng;
-        rng.pixel = pixel;
-        rng.k0 = A.k0;
-        rng.k1 = A.k1;
-        rng.sample = 0;
-        Ray ray;
-        V3 L = v3(0, 0, 0), T = v3(1, 1, 1);
-        uint32_t bounce = 0, origin_prim = PRIM_NONE;
-        bool alive = false;
-
-        while (true) {
-            if (!alive) {
-                if (s >= s_end) break;
-                rng.sample = (uint32_t)(A.spp_begin + A.sample_offset + s * A.sample_stride);
-                ray = camera_ray(S, px, py, rng);
-                L = v3(0, 0, 0);
-                T = v3(1, 1, 1);
-                bounce = 0;
-                origin_prim = PRIM_NONE;
-                alive = true;
-                if (STATS) st.samples++;
-            }
-            // ---- one bounce: Camera.txt:203-238 ------------------------------------
-            Hit hit;
-            traverse<STATS>(S, ray, 0.001f, __int_as_float(0x7f800000), origin_prim, hit, &st, &overflow);
-            int medium = -1;
-            if (S.n_media > 0) medium = media_hit<STATS>(S, ray, 0.001f, hit.t, rng, bounce, &st);
-
-            bool done = false;
-            if (medium < 0 && hit.prim == PRIM_NONE) {
-                L = L + T * v3(S.background);
-                done = true;
-            } else {
-                Surface sf;
-                if (medium >= 0) {  // constant_medium.h:45-50
-                    const DevMedium& md = S.media[medium];
-                    sf.p = fma3(hit.t, ray.d, ray.o);
-                    sf.normal = v3(md.normal);
-                    sf.front = true;
-                    sf.u = sf.v = 0.0f;
-                    sf.material = md.material;
-                    sf.prim_id = -1;
-                    origin_prim = PRIM_NONE;
-                } else {
-                    complete_hit(S, ray, hit, sf, false);
-                    origin_prim = hit.prim;
-                }
-                const DevMaterial& m = S.mats[sf.material];
-                float4 u4 = make_float4(0, 0, 0, 0);
-                if (m.type != RT_MAT_DIFFUSE_LIGHT && m.type != RT_MAT_EMISSIVE_LIGHT) u4 = rng.draw(bounce, RS_SCATTER);
-                V3 att, emitted;
-                Ray next;
-                const bool scattered = shade_surface(S, m, ray, sf, u4, emitted, att, next);
-                L = L + T * emitted;
-                if (!scattered) {
-                    done = true;
-                } else {
-                    if (S.n_lights > 0) L = L + T * att * point_lighting(S, sf.p, sf.normal);
-                    T = T * att;
-                    ray = next;
-                    bounce++;
-                    if (bounce >= (uint32_t)A.max_depth) done = true;  // ray_color(depth <= 0) returns 0
-                }
-            }
-            if (done) {
-                const bool finite = isfinite(L.x) && isfinite(L.y) && isfinite(L.z);
-                if (finite) {
-                    sum_r += __float2ull_rn(fminf(fmaxf(L.x, 0.0f), kSampleClamp) * kAccumScale);
-                    sum_g += __float2ull_rn(fminf(fmaxf(L.y, 0.0f), kSampleClamp) * kAccumScale);
-                    sum_b += __float2ull_rn(fminf(fmaxf(L.z, 0.0f), kSampleClamp) * kAccumScale);
-                } else {
-                    dropped++;
-                }
-                alive = false;
-                s++;
-            }
-        }
-        if (inside) {
-            unsigned long long* a = accum + 4ull * pixel;
-            atomicAdd(a + 0, sum_r);
-            atomicAdd(a + 1, sum_g);
-            atomicAdd(a + 2, sum_b);
-            if (dropped) { atomicAdd(a + 3, dropped); }
-        }
-        if (STATS) st.nonfinite += dropped;
-        dropped = 0;
-        __syncwarp();
-    }
-    if (overflow) atomicAdd(&counters[1], 1ull);
-    if (STATS) {
-        unsigned long long* g = reinterpret_cast<unsigned long long*>(gstats);
-        const unsigned long long* l = reinterpret_cast<const unsigned long long*>(&st);
-        for (unsigned i = 0; i < sizeof(Stats) / 8; i++) {
-            unsigned long long v = l[i];
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-            if (lane == 0 && v) atomicAdd(g + i, v);
-        }
-    }
-}
+#ifdef RT_B200_ALT_KERNELS
+#include "rt_kernel_v1.cuh"
+#endif
 
 // ---------------------------------------------------------------------------------
 // render_kernel_v2 — the production megakernel.
@@ -213,8 +89,14 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Dev
 #ifndef RT_TRAV_THRESHOLD
 #define RT_TRAV_THRESHOLD 4
 #endif
+#ifndef RT_B200_DEFAULT_BVH_WIDTH
+#define RT_B200_DEFAULT_BVH_WIDTH 2  // the default is decided by measurement
+#endif
 #ifndef RT_MIN_BLOCKS
 #define RT_MIN_BLOCKS 3
+#endif
+#ifndef RT_WIDE_MIN_BLOCKS
+#define RT_WIDE_MIN_BLOCKS RT_MIN_BLOCKS  // blocks per SM the wide instances are compiled for (register budget)
 #endif
 #ifndef RT_V2_THREADS
 #define RT_V2_THREADS 256  // threads per block of render_kernel_v2 (tuning experiments: 224 x 3 trades warps for registers)
@@ -230,15 +112,22 @@ constexpr int kTravThreshold = RT_TRAV_THRESHOLD;
 constexpr int kDescendDiv = RT_DESCEND_DIV;
 enum : int { LANE_IDLE = 0, LANE_TRAVERSE = 1, LANE_SHADE = 2 };
 
-template <bool STATS, bool LITE, bool NEE = false>
-__global__ void __launch_bounds__(RT_V2_THREADS, RT_MIN_BLOCKS) render_kernel_v2(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A,
+// WIDTH: which acceleration structure the instance traverses -- 2: the binary tree of 64-byte nodes
+// (Trav, stack in local memory), 8 / 4: the wide quantised tree (TravW, rt_wide.cuh; stack in dynamic
+// shared memory, [entry][thread], `A.stack_entries` entries per thread)
+template <int WIDTH>
+struct TravSel { using Trav = TravW<WIDTH>; using RayConst = RayConstW; };
+template <>
+struct TravSel<2> { using Trav = rtdev::Trav; using RayConst = rtdev::RayConst; };
+
+template <bool STATS, bool LITE, bool NEE = false, int WIDTH = 2>
+__global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT_WIDE_MIN_BLOCKS) render_kernel_v2(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A,
                                                         unsigned long long* __restrict__ accum,
                                                         unsigned long long* __restrict__ counters, Stats* __restrict__ gstats) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     Stats st;
     if (STATS) memset(&st, 0, sizeof st);
-    int overflow = 0;
 
     // warp-uniform pool of (pixel, sample) pairs
     unsigned pool_pos = 0, pool_size = 0;
@@ -256,10 +145,14 @@ __global__ void __launch_bounds__(RT_V2_THREADS, RT_MIN_BLOCKS) render_kernel_v2
     V3 L = v3(0, 0, 0), T = v3(1, 1, 1);
     uint32_t bounce = 0, origin_prim = PRIM_NONE;
     float nee_pdf = 0.0f;  // NEE: > 0 when the previous vertex sampled the listed emitters directly: the density of the direction it scattered into
-    Trav tr;
-    StackEntry stack[STACK_SIZE];
-    tr.cur = LINK_DONE;
-    tr.sp = 0;
+    typename TravSel<WIDTH>::Trav tr;
+    StackEntry stack_mem[WIDTH == 2 ? STACK_SIZE : 1];
+    extern __shared__ uint2 wide_stack_mem[];
+    auto stack = [&]() {
+        if constexpr (WIDTH == 2) return &stack_mem[0];
+        else return SmemStack<RT_V2_THREADS>::make(wide_stack_mem);
+    }();
+    tr.clear();
     tr.hit.t = 0;
     tr.hit.prim = PRIM_NONE;
     tr.hit.u = tr.hit.v = 0;
@@ -314,7 +207,7 @@ __global__ void __launch_bounds__(RT_V2_THREADS, RT_MIN_BLOCKS) render_kernel_v2
 
         // ---- 2. traversal phase ------------------------------------------------------------------
         {
-            RayConst rc;
+            typename TravSel<WIDTH>::RayConst rc;
             rc.set(ray);
             while (true) {
                 // descend: every traversing lane that holds an interior node takes one step per
@@ -324,7 +217,7 @@ __global__ void __launch_bounds__(RT_V2_THREADS, RT_MIN_BLOCKS) render_kernel_v2
                 while (true) {
                     // a lane that is not traversing holds LINK_DONE (negative), so the link alone says who
                     // descends; the vote goes straight to a predicate (two instructions fewer per step: +1.2 % on C5)
-                    const bool descending = tr.cur >= 0;
+                    const bool descending = tr.wants_node();
                     if (!STATS && kDescendDiv == 0) {
                         if (!__any_sync(0xffffffffu, descending)) break;
                     }
@@ -336,7 +229,7 @@ __global__ void __launch_bounds__(RT_V2_THREADS, RT_MIN_BLOCKS) render_kernel_v2
                         if (lane == 0) { st.desc_iters++; st.desc_lanes += __popc(dmask); st.desc_trav_lanes += __popc(tmask); }
                     }
                     if (descending) {
-                        tr.interior<STATS>(S, rc, 0.001f, stack, &st, &overflow);
+                        tr.template node_step<STATS>(S, ray, rc, 0.001f, stack, &st);
                         if (STATS) {
                             seg_steps++;
                             if (tr.done()) {
@@ -347,12 +240,12 @@ __global__ void __launch_bounds__(RT_V2_THREADS, RT_MIN_BLOCKS) render_kernel_v2
                     }
                 }
                 if (STATS) {
-                    const unsigned lmask = __ballot_sync(0xffffffffu, state == LANE_TRAVERSE && tr.cur < 0 && !tr.done());
+                    const unsigned lmask = __ballot_sync(0xffffffffu, state == LANE_TRAVERSE && !tr.wants_node() && !tr.done());
                     if (lane == 0 && lmask) { st.leaf_iters++; st.leaf_lanes += __popc(lmask); }
                 }
-                if (state == LANE_TRAVERSE && tr.cur < 0) {
+                if (state == LANE_TRAVERSE && !tr.wants_node()) {
                     if (!tr.done()) {
-                        tr.leaf<STATS, LITE>(S, ray, rc, 0.001f, origin_prim, stack, &st);
+                        tr.template leaf_step<STATS, LITE>(S, ray, rc, 0.001f, origin_prim, stack, &st);
                         if (STATS) {
                             atomicAdd(hist + (n_leaf ? 64 : 0) + min(seg_steps, 63u), 1ull);
                             n_leaf++;
@@ -419,7 +312,7 @@ __global__ void __launch_bounds__(RT_V2_THREADS, RT_MIN_BLOCKS) render_kernel_v2
                     done = true;
                 } else {
                     if (!LITE && S.n_lights > 0) {
-                        if (NEE && A.shadow_point_lights) L = L + T * att * point_lighting_shadowed(S, sf.p, sf.normal, origin_prim, ray.time, &counters[1]);
+                        if (NEE && A.shadow_point_lights) L = L + T * att * point_lighting_shadowed<WIDTH>(S, sf.p, sf.normal, origin_prim, ray.time);
                         else L = L + T * att * point_lighting(S, sf.p, sf.normal);
                     }
                     if (NEE) {
@@ -427,7 +320,7 @@ __global__ void __launch_bounds__(RT_V2_THREADS, RT_MIN_BLOCKS) render_kernel_v2
                         if (A.nee_emitters && S.n_nee_lights > 0 && (m.type == RT_MAT_LAMBERTIAN || m.type == RT_MAT_ISOTROPIC)) {
                             const bool iso = m.type == RT_MAT_ISOTROPIC;
                             nee_pdf = scatter_density(normalize(next.d), sf.normal, iso);
-                            L = L + T * att * nee_direct(S, sf.p, sf.normal, iso, origin_prim, ray.time, rng.draw(bounce, RS_NEE), &counters[1]);
+                            L = L + T * att * nee_direct<WIDTH>(S, sf.p, sf.normal, iso, origin_prim, ray.time, rng.draw(bounce, RS_NEE));
                         }
                     }
                     T = T * att;
@@ -454,7 +347,6 @@ __global__ void __launch_bounds__(RT_V2_THREADS, RT_MIN_BLOCKS) render_kernel_v2
             }
         }
     }
-    if (overflow) atomicAdd(&counters[1], 1ull);
     if (STATS) {
         unsigned long long* g = reinterpret_cast<unsigned long long*>(gstats);
         const unsigned long long* l = reinterpret_cast<const unsigned long long*>(&st);
@@ -466,7 +358,16 @@ __global__ void __launch_bounds__(RT_V2_THREADS, RT_MIN_BLOCKS) render_kernel_v2
     }
 }
 
+#ifdef RT_B200_ALT_KERNELS
 #include "rt_kernel_v3.cuh"
+#endif
+
+// one ray through whichever acceleration structure the scene was uploaded with (test kernels)
+__device__ __forceinline__ void traverse_uploaded(const DevScene& S, const Ray& ray, float tmin, float tmax, Hit& hit) {
+    if (S.wide_width == 8) traverse_sel<8>(S, ray, tmin, tmax, PRIM_NONE, hit);
+    else if (S.wide_width == 4) traverse_sel<4>(S, ray, tmin, tmax, PRIM_NONE, hit);
+    else traverse_sel<2>(S, ray, tmin, tmax, PRIM_NONE, hit);
+}
 
 __global__ void aov_kernel(const __grid_constant__ DevScene S, int width, int height, int* __restrict__ prim_id,
                            float* __restrict__ t_out, float* __restrict__ normal, float* __restrict__ point,
@@ -478,9 +379,7 @@ __global__ void aov_kernel(const __grid_constant__ DevScene S, int width, int he
     ray.d = fma3((float)i, v3(S.du), fma3((float)j, v3(S.dv), v3(S.dir00)));
     ray.time = 0.0f;
     Hit hit;
-    int overflow = 0;
-    traverse<false>(S, ray, 0.001f, __int_as_float(0x7f800000), PRIM_NONE, hit, nullptr, &overflow);
-    if (overflow) atomicAdd(&counters[1], 1ull);
+    traverse_uploaded(S, ray, 0.001f, __int_as_float(0x7f800000), hit);
     size_t px = (size_t)j * width + i;
     Surface sf;
     sf.prim_id = -1;
@@ -558,9 +457,7 @@ __global__ void probe_hit_kernel(const __grid_constant__ DevScene S, int n, cons
     Ray ray;
     ray.o = v3(r); ray.d = v3(r + 3); ray.time = r[6];
     Hit hit;
-    int overflow = 0;
-    traverse<false>(S, ray, r[7], r[8], PRIM_NONE, hit, nullptr, &overflow);
-    if (overflow) atomicAdd(&counters[1], 1ull);
+    traverse_uploaded(S, ray, r[7], r[8], hit);
     Surface sf;
     sf.prim_id = -1;
     sf.normal = v3(0, 0, 0);
@@ -621,11 +518,17 @@ struct rt_ctx {
     rt_stats stats{};
     int cam_w = 0, cam_h = 0;  // frame the device camera block was computed for
     int sm_count = 0;
-    int kernel_version = 2;  // RT_B200_KERNEL=v1 | v2 | wf: which formulation of the bounce loop runs (A/B measurements)
+    int kernel_version = 2;  // 2 = render_kernel_v2; with -DRT_B200_ALT_KERNELS RT_B200_KERNEL=v1 | v3 | wf select the measured alternatives
+#ifdef RT_B200_ALT_KERNELS
     rtwf::Pool pool{};       // wavefront path pool (allocated on first use)
     void* pool_mem = nullptr;
     int wf_blocks_per_sm[2] = {0, 0};
+#endif
     int blocks_per_sm[2] = {0, 0};
+    // acceleration structure the render kernels traverse: 2 = binary tree, 8 / 4 = wide quantised tree
+    // (host-built scenes only; a device-built scene keeps the binary tree).  rt_set_bvh_width / RT_B200_BVH_WIDTH
+    int bvh_width = RT_B200_DEFAULT_BVH_WIDTH;
+    int wide_depth = 0;  // levels of the uploaded wide tree = stack entries a ray can need
     bool pending_async = false;
     // scene-upload path: 0 auto (device from kDeviceBuildAuto primitives up), 1 host SAH, 2 device (LBVH + SAH top levels), 3 device, pure LBVH
     int bvh_builder = 0;
@@ -640,6 +543,8 @@ struct rt_ctx {
 // per-cluster SAH rebuild and the SAH top levels the device-built tree traces within -1...-12 % of
 // the host's.  Every BASELINE scene is smaller and keeps the host tree.
 constexpr int kDeviceBuildAuto = 1 << 16;
+// the wide kernels keep their traversal stack in shared memory: 8 bytes x threads x levels per block
+constexpr int kWideMaxDepth = 24;
 constexpr int kDeviceBuildMin = 8;
 
 static int fail(rt_ctx* ctx, int code, const char* fmt, ...) {
@@ -666,9 +571,11 @@ static void release_buffers(rt_ctx* ctx) {
     ctx->copy_ring.release();
     ctx->scratch = nullptr;
     ctx->scratch_cap = 0;
+#ifdef RT_B200_ALT_KERNELS
     if (ctx->pool_mem) cudaFree(ctx->pool_mem);
     ctx->pool_mem = nullptr;
     ctx->pool = rtwf::Pool{};
+#endif
     if (ctx->staging) cudaFreeHost(ctx->staging);
     if (ctx->out_lin) cudaFree(ctx->out_lin);
     if (ctx->out_rgb8) cudaFree(ctx->out_rgb8);
@@ -711,9 +618,8 @@ extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
     CU(ctx, cudaEventCreate(&ctx->ev1));
     CU(ctx, cudaMalloc(&ctx->counters, 4 * sizeof(unsigned long long)));
     CU(ctx, cudaMalloc(&ctx->dstats, sizeof(Stats) + kTravHistBins * sizeof(unsigned long long)));
-    // local-memory traversal stacks live in L1: prefer L1 over shared memory
-    cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    // local-memory traversal stacks live in L1: prefer L1 over shared memory (the wide instances
+    // get their carve-out per launch, from the depth of the uploaded tree)
     cudaFuncSetAttribute(render_kernel_v2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -721,8 +627,17 @@ extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
     cudaFuncSetAttribute(render_kernel_v2<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     if (const char* bv = getenv("RT_B200_BVH"))
         ctx->bvh_builder = strcmp(bv, "host") == 0 ? 1 : (strcmp(bv, "device") == 0 ? 2 : (strcmp(bv, "lbvh") == 0 ? 3 : 0));
+    if (const char* wv = getenv("RT_B200_BVH_WIDTH")) {
+        const int w = atoi(wv);
+        if (w != 2 && w != 4 && w != 8) return fail(ctx, RT_ERR_INVALID, "RT_B200_BVH_WIDTH=%s: 2, 4 or 8", wv);
+        ctx->bvh_width = w;
+    }
+    cudaFuncAttributes fa;
+#ifdef RT_B200_ALT_KERNELS
     if (const char* kv = getenv("RT_B200_KERNEL"))
         ctx->kernel_version = strcmp(kv, "v1") == 0 ? 1 : (strcmp(kv, "wf") == 0 ? 3 : (strcmp(kv, "v3") == 0 ? 4 : 2));
+    cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     // v3 parks one path context per lane in shared memory: 23.5 KB per block, three blocks per SM
     cudaFuncSetAttribute(render_kernel_v3<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 40);
     cudaFuncSetAttribute(render_kernel_v3<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 40);
@@ -733,7 +648,6 @@ extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
     cudaFuncSetAttribute(rtwf::wf_shade<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->wf_blocks_per_sm[0], rtwf::wf_extend<false>, 256, 0));
     CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->wf_blocks_per_sm[1], rtwf::wf_shade<false>, 256, 0));
-    cudaFuncAttributes fa;
     if (ctx->kernel_version == 1) {
         CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], render_kernel<false>, 256, 0));
         CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], render_kernel<true>, 256, 0));
@@ -742,7 +656,13 @@ extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
         CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], render_kernel_v3<false, false>, 256, 0));
         CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], render_kernel_v3<true, false>, 256, 0));
         CU(ctx, cudaFuncGetAttributes(&fa, render_kernel_v3<false, false>));
-    } else {
+    } else
+#else
+    if (const char* kv = getenv("RT_B200_KERNEL"))
+        if (strcmp(kv, "v2") != 0)
+            return fail(ctx, RT_ERR_UNSUPPORTED, "RT_B200_KERNEL=%s: the alternative kernels are compiled only with -DRT_B200_ALT_KERNELS (build.py --alt)", kv);
+#endif
+    {
         CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], render_kernel_v2<false, false>, RT_V2_THREADS, 0));
         CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], render_kernel_v2<true, false>, RT_V2_THREADS, 0));
         CU(ctx, cudaFuncGetAttributes(&fa, render_kernel_v2<false, false>));
@@ -1119,6 +1039,28 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
     static_assert(sizeof(rtbvh::Node) == 64, "node layout");
     std::memcpy(nodes.data(), bvh.nodes.data(), bvh.nodes.size() * 64);
 
+    // ---- the wide quantised tree, collapsed from the SAH BVH2 (host-built scenes) -----------------
+    rtwide::Built wide;
+    if (!device_build && ctx->bvh_width != 2 && sc->n_world > 0) {
+        float wlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, whi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (int i = 0; i < sc->n_world; i++) {
+            float lo[3], hi[3];
+            rtprep::prim_bounds(baked[i], lo, hi);
+            for (int k = 0; k < 3; k++) {
+                const float e = 1e-6f * std::max({1.0f, std::fabs(lo[k]), std::fabs(hi[k])});
+                wlo[k] = std::min(wlo[k], lo[k] - e);
+                whi[k] = std::max(whi[k], hi[k] + e);
+            }
+        }
+        rtwide::CollapseTuning wt;  // RT_B200_WIDE_*: tuning experiments only
+        if (const char* e = getenv("RT_B200_WIDE_NODE_COST")) wt.node_cost = (float)atof(e);
+        if (const char* e = getenv("RT_B200_WIDE_GRID_STEPS")) wt.grid_steps = (float)atof(e);
+        if (const char* e = getenv("RT_B200_WIDE_SCALE_AWARE")) wt.scale_aware = atoi(e) != 0;
+        if (ctx->bvh_width == 8) rtwide::build_wide<8>(bvh, true, wlo, whi, wide, wt);
+        else rtwide::build_wide<4>(bvh, true, wlo, whi, wide, wt);
+        if (wide.depth > (uint32_t)kWideMaxDepth) wide = rtwide::Built();  // degenerate tree: keep the binary one
+    }
+
     DevScene& S = ctx->scene;
     std::memset(&S, 0, sizeof S);
     // ---- one arena.  Host path: everything is staged in pinned memory at its arena offset and moved
@@ -1143,6 +1085,10 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
 #define UP(vec, field) add_block(vec.data(), vec.size() * sizeof(vec[0]), 0, (const void**)&S.field);
 #define UPW(vec, field, type, rec_bytes) add_block(vec.data(), vec.size() * sizeof(vec[0]), world_count[type] * (size_t)(rec_bytes), (const void**)&S.field);
     add_block(nodes.data(), device_build ? 0 : nodes.size() * sizeof(float4), node_skip, (const void**)&S.nodes);
+    if (wide.n_nodes) {
+        add_block(wide.words.data(), wide.words.size() * sizeof(uint32_t), 0, (const void**)&S.wnodes);
+        add_block(wide.refs.data(), wide.refs.size() * sizeof(int32_t), 0, (const void**)&S.wrefs);
+    }
     UPW(sph, sph, PT_SPHERE, 16) UPW(msph, msph, PT_MSPHERE, 32) UPW(quad, quad, PT_QUAD, 48) UPW(tri, tri, PT_TRI, 48)
     UPW(sph_d, sph_d, PT_SPHERE, 32) UPW(msph_d, msph_d, PT_MSPHERE, 64) UPW(quad_d, quad_d, PT_QUAD, 96) UPW(tri_d, tri_d, PT_TRI, 72)
     UPW(sph_sh, sph_sh, PT_SPHERE, 16) UPW(msph_sh, msph_sh, PT_MSPHERE, 16) UPW(quad_sh, quad_sh, PT_QUAD, 16) UPW(tri_sh, tri_sh, PT_TRI, 48)
@@ -1232,6 +1178,13 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
     S.n_lights = sc->n_lights;
     S.n_nee_lights = (int)nee_lights.size();
     S.nee_total_area = (float)nee_area;
+    S.wide_width = wide.n_nodes ? wide.width : 0;
+    S.f32_one_bits = 0x3F800000u;
+    if (!wide.n_nodes) { S.wnodes = nullptr; S.wrefs = nullptr; }
+    ctx->wide_depth = (int)wide.depth;
+    ctx->stats.bvh_width = wide.n_nodes ? (uint32_t)wide.width : 2u;
+    ctx->stats.wide_nodes = wide.n_nodes;
+    ctx->stats.wide_depth = wide.depth;
     ctx->camera = sc->camera;
     ctx->scene_lite = tri.empty() && world_count[PT_TRI] == 0 && sc->n_lights == 0 && !(sc->camera.defocus_angle > 0);
     ctx->cam_w = ctx->cam_h = 0;
@@ -1266,6 +1219,14 @@ extern "C" int rt_set_bvh_builder(rt_ctx* ctx, int32_t mode) {
     if (!ctx) return RT_ERR_INVALID;
     if (mode < 0 || mode > 3) return fail(ctx, RT_ERR_INVALID, "rt_set_bvh_builder: mode %d (0 auto, 1 host, 2 device, 3 device without the SAH top)", mode);
     ctx->bvh_builder = mode;
+    return RT_OK;
+}
+
+// 2, 4 or 8: which acceleration structure the next rt_upload_scene builds for the render kernels
+extern "C" int rt_set_bvh_width(rt_ctx* ctx, int32_t width) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (width != 2 && width != 4 && width != 8) return fail(ctx, RT_ERR_INVALID, "rt_set_bvh_width: %d (2 binary, 4 or 8 wide quantised)", width);
+    ctx->bvh_width = width;
     return RT_OK;
 }
 
@@ -1362,6 +1323,7 @@ extern "C" int rt_sync(rt_ctx* ctx) {
 // wavefront driver (RT_B200_KERNEL=wf): generate once, then (swap, extend, shade) per bounce
 // of the pool until the sample stream is exhausted and no path is alive
 // ---------------------------------------------------------------------------------
+#ifdef RT_B200_ALT_KERNELS
 static int launch_wavefront(rt_ctx* ctx, const RenderArgs& A, cudaStream_t stream, bool stats, unsigned long long pixel_blocks) {
     rtwf::Stream W;
     std::memset(&W, 0, sizeof W);
@@ -1422,6 +1384,57 @@ static int launch_wavefront(rt_ctx* ctx, const RenderArgs& A, cudaStream_t strea
     ctx->stats.kernel_launches = launches;
     return RT_OK;
 }
+#endif
+
+// The instances of render_kernel_v2: variant 0 plain, 1 LITE, 2 STATS, 3 NEE + LITE, 4 NEE; width 2, 4, 8.
+typedef void (*RenderKernel)(const DevScene, const RenderArgs, unsigned long long*, unsigned long long*, Stats*);
+template <int WIDTH>
+static RenderKernel v2_instance(int variant) {
+    switch (variant) {
+        case 1: return render_kernel_v2<false, true, false, WIDTH>;
+        case 2: return render_kernel_v2<true, false, false, WIDTH>;
+        default: return render_kernel_v2<false, false, false, WIDTH>;
+    }
+}
+// the opt-in NEE instances exist for the binary tree only (every scene has one; shadow rays and paths
+// then both go through it): two fat kernels less per width in the shipped library
+static int v2_effective_width(int variant, int width) { return variant >= 3 ? 2 : width; }
+static RenderKernel v2_kernel(int variant, int width) {
+    if (variant == 3) return render_kernel_v2<false, true, true, 2>;
+    if (variant == 4) return render_kernel_v2<false, false, true, 2>;
+    return width == 8 ? v2_instance<8>(variant) : (width == 4 ? v2_instance<4>(variant) : v2_instance<2>(variant));
+}
+// dynamic shared memory of a wide instance: the traversal stacks, [entry][thread]
+static size_t v2_smem(const rt_ctx* ctx, int width) { return width <= 2 ? 0 : (size_t)std::max(ctx->wide_depth, 1) * RT_V2_THREADS * sizeof(uint2); }
+
+// blocks per SM the kernel instance runs with (the grid is persistent: SMs x this)
+static int v2_blocks_per_sm(rt_ctx* ctx, int variant, int width, int* out) {
+    width = v2_effective_width(variant, width);
+    RenderKernel k = v2_kernel(variant, width);
+    const size_t smem = v2_smem(ctx, width);
+    if (width != 2) {
+        // carve out what RT_MIN_BLOCKS blocks need (plus the 1 KB the system reserves per block), the rest stays L1
+        const int pct = (int)std::min<size_t>(100, (100 * RT_WIDE_MIN_BLOCKS * (smem + 1024) + 233471) / 233472);
+        CU(ctx, cudaFuncSetAttribute((const void*)k, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, (const void*)k, RT_V2_THREADS, smem));
+    return RT_OK;
+}
+
+static int launch_v2(rt_ctx* ctx, int variant, int width, int grid, const RenderArgs& A, cudaStream_t stream) {
+    width = v2_effective_width(variant, width);
+    size_t smem = v2_smem(ctx, width);
+    // RT_B200_DUMMY_SMEM: unused dynamic shared memory per block, to measure what giving up
+    // that much L1 would cost (tuning experiment, binary kernel only)
+    if (width == 2)
+        if (const char* e = getenv("RT_B200_DUMMY_SMEM")) {
+            smem = (size_t)atoi(e);
+            const int pct = (int)std::min<size_t>(100, (100 * 3 * (smem + 1024) + 233471) / 233472);
+            cudaFuncSetAttribute((const void*)v2_kernel(variant, 2), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
+    v2_kernel(variant, width)<<<grid, RT_V2_THREADS, smem, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+    return RT_OK;
+}
 
 extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
     if (!ctx) return RT_ERR_INVALID;
@@ -1473,7 +1486,11 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
         return fail(ctx, RT_ERR_INVALID, "rt_render: unknown shard_mode %d", p->shard_mode);
     }
     const bool stats = (p->flags & RT_FLAG_STATS) != 0;
-    const int bps = ctx->blocks_per_sm[stats ? 1 : 0];
+    int bps = ctx->blocks_per_sm[stats ? 1 : 0];
+    if (ctx->kernel_version == 2 && ctx->scene.wide_width && !(p->flags & (RT_FLAG_NEE | RT_FLAG_SHADOWED_POINT_LIGHTS))) {
+        rc = v2_blocks_per_sm(ctx, stats ? 2 : 0, ctx->scene.wide_width, &bps);
+        if (rc != RT_OK) return rc;
+    }
     const int grid = ctx->sm_count * (bps > 0 ? bps : 1);
     // segment length: enough work items to keep every resident warp busy ~64 times over,
     // but never shorter than 1 sample (fixed-point sums make the split result-neutral)
@@ -1500,6 +1517,7 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
     if (!async) CU(ctx, cudaEventRecord(ctx->ev0, stream));
     ctx->stats.kernel_launches = 0;
     if (A.n_items > 0) {
+#ifdef RT_B200_ALT_KERNELS
         if (ctx->kernel_version == 3) {
             rc = launch_wavefront(ctx, A, stream, stats, pixel_blocks);
             if (rc != RT_OK) return rc;
@@ -1511,26 +1529,17 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
             if (stats) render_kernel_v3<true, false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
             else if (lite) render_kernel_v3<false, true><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
             else render_kernel_v3<false, false><<<grid, 256, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
-        } else {
+        } else
+#endif
+        {
             // LITE: no triangles, no point lights, no defocus blur in this scene (see hit_prim)
             const bool lite = ctx->scene_lite && !getenv("RT_B200_NO_LITE");
-            // RT_B200_DUMMY_SMEM: unused dynamic shared memory per block, to measure what giving up
-            // that much L1 would cost (tuning experiment)
-            size_t dummy = 0;
-            if (const char* e = getenv("RT_B200_DUMMY_SMEM")) {
-                dummy = (size_t)atoi(e);
-                int pct = (int)std::min<size_t>(100, (100 * 3 * (dummy + 1024) + 233471) / 233472);
-                cudaFuncSetAttribute(render_kernel_v2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-                cudaFuncSetAttribute(render_kernel_v2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            }
             A.nee_emitters = (p->flags & RT_FLAG_NEE) != 0 && ctx->scene.n_nee_lights > 0;
             A.shadow_point_lights = (p->flags & RT_FLAG_SHADOWED_POINT_LIGHTS) != 0 && ctx->scene.n_lights > 0;
             const bool nee = A.nee_emitters || A.shadow_point_lights;
-            if (nee && lite) render_kernel_v2<false, true, true><<<grid, RT_V2_THREADS, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
-            else if (nee) render_kernel_v2<false, false, true><<<grid, RT_V2_THREADS, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
-            else if (stats) render_kernel_v2<true, false><<<grid, RT_V2_THREADS, 0, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
-            else if (lite) render_kernel_v2<false, true><<<grid, RT_V2_THREADS, dummy, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
-            else render_kernel_v2<false, false><<<grid, RT_V2_THREADS, dummy, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+            const int variant = nee ? (lite ? 3 : 4) : (stats ? 2 : (lite ? 1 : 0));
+            rc = launch_v2(ctx, variant, ctx->scene.wide_width ? ctx->scene.wide_width : 2, grid, A, stream);
+            if (rc != RT_OK) return rc;
         }
         CU(ctx, cudaGetLastError());
         if (ctx->kernel_version != 3) ctx->stats.kernel_launches = 1;
@@ -1571,6 +1580,7 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
         ctx->stats.medium_queries = h.medium_queries;
         ctx->stats.boundary_tests = h.boundary_tests;
         ctx->stats.fp64_sphere_tests = h.fp64_sphere;
+        ctx->stats.empty_node_steps = h.empty_steps;
         ctx->stats.nonfinite_samples = h.nonfinite;
         ctx->stats.desc_iters = h.desc_iters;
         ctx->stats.desc_lanes = h.desc_lanes;

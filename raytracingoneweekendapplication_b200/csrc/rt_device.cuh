@@ -80,6 +80,12 @@ struct DevScene {
     int root;
     int n_nodes;
     int n_world;  // 0: every ray misses (the root link is not followed)
+    // the W-wide quantised BVH collapsed from `nodes` (bvh_wide.h; null when the scene has none):
+    // W = 8: 5 uint4 per node, W = 4: 3; wrefs[W * node + slot] = BVH2 leaf link of a leaf child
+    const void* wnodes;
+    const int32_t* wrefs;
+    int wide_width;  // 0, 4 or 8
+    uint32_t f32_one_bits;  // 0x3F800000, as a kernel parameter the compiler cannot fold (rt_wide.cuh, unit_plus_byte)
     const float4* sph;
     const float4* msph;
     const float4* quad;
@@ -117,6 +123,7 @@ struct Stats {
         boundary_tests, fp64_sphere, nonfinite, samples;
     // lane occupancy of render_kernel_v2's phases, counted per warp-level iteration (lane 0 adds)
     unsigned long long desc_iters, desc_lanes, desc_trav_lanes, leaf_iters, leaf_lanes, shade_iters, shade_lanes;
+    unsigned long long empty_steps;  // node steps in which no child box was hit
 };
 
 // ---------------------------------------------------------------------------------
@@ -363,6 +370,9 @@ struct Trav {
         cur = S.n_world > 0 ? S.root : LINK_DONE;
     }
     __device__ __forceinline__ bool done() const { return cur == LINK_DONE; }
+    // the interface render_kernel_v2 shares with the wide traversal (rt_wide.cuh)
+    __device__ __forceinline__ void clear() { cur = LINK_DONE; sp = 0; }
+    __device__ __forceinline__ bool wants_node() const { return cur >= 0; }
 
     // pop, skipping subtrees that start beyond the closest hit so far
     __device__ __forceinline__ void pop(const StackEntry* stack) {
@@ -397,6 +407,7 @@ struct Trav {
         float rn = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), tmin));
         float rf = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), hit.t));
         const bool hl = ln <= lf, hr = rn <= rf;
+        if (STATS && !hl && !hr) st->empty_steps++;
         const int linkl = __float_as_int(a.w), linkr = __float_as_int(b.w);
         const bool right_first = hr && (!hl || rn < ln);
         const int near_l = right_first ? linkr : linkl;
@@ -420,6 +431,16 @@ struct Trav {
         uint32_t type = v >> 28, cnt = ((v >> 25) & 7u) + 1u, first = v & 0x1ffffffu;
         for (uint32_t i = 0; i < cnt; i++) hit_prim<STATS, LITE>(S, type, first + i, ray, rc.inv_a, tmin, origin_prim, hit, st);
         pop(stack);
+    }
+
+    template <bool STATS>
+    __device__ __forceinline__ void node_step(const DevScene& S, const Ray&, const RayConst& rc, float tmin, StackEntry* stack, Stats* st) {
+        interior<STATS>(S, rc, tmin, stack, st, nullptr);
+    }
+    template <bool STATS, bool LITE>
+    __device__ __forceinline__ void leaf_step(const DevScene& S, const Ray& ray, const RayConst& rc, float tmin, uint32_t origin_prim,
+                                              const StackEntry* stack, Stats* st) {
+        leaf<STATS, LITE>(S, ray, rc, tmin, origin_prim, stack, st);
     }
 };
 
@@ -895,10 +916,25 @@ __device__ __forceinline__ float media_transmittance(const DevScene& S, const Ra
     return __expf(-optical_depth);
 }
 
+// shadow rays go through whichever acceleration structure the kernel instance traverses
+// (traverse_wide is defined in rt_wide.cuh)
+template <int W, bool STATS>
+__device__ __forceinline__ void traverse_wide(const DevScene& S, const Ray& ray, float tmin, float tmax, uint32_t origin_prim, Hit& hit,
+                                              Stats* st);
+template <int WIDTH>
+__device__ __forceinline__ void traverse_sel(const DevScene& S, const Ray& ray, float tmin, float tmax, uint32_t origin_prim, Hit& hit) {
+    if constexpr (WIDTH == 2) {
+        int ov = 0;
+        traverse<false>(S, ray, tmin, tmax, origin_prim, hit, nullptr, &ov);
+    } else {
+        traverse_wide<WIDTH, false>(S, ray, tmin, tmax, origin_prim, hit, nullptr);
+    }
+}
+
 // The directly-lit part of one lambertian / isotropic scattering event at p: radiance per unit of
 // (throughput * albedo).  `u` = three uniforms (which emitter, where on it).
-__device__ __noinline__ V3 nee_direct(const DevScene& S, V3 p, V3 n, bool isotropic, uint32_t origin_prim, float time, float4 u,
-                                      unsigned long long* overflow_flag) {
+template <int WIDTH>
+__device__ __noinline__ V3 nee_direct(const DevScene& S, V3 p, V3 n, bool isotropic, uint32_t origin_prim, float time, float4 u) {
     int k = 0;
     while (k + 1 < S.n_nee_lights && u.x >= S.nee_lights[k].cdf) k++;
     const DevNeeLight& lt = S.nee_lights[k];
@@ -918,9 +954,7 @@ __device__ __noinline__ V3 nee_direct(const DevScene& S, V3 p, V3 n, bool isotro
     sray.time = time;
     const float tmax = r * (1.0f - 1e-4f);
     Hit h;
-    int ov = 0;
-    traverse<false>(S, sray, 0.001f, tmax, origin_prim, h, nullptr, &ov);
-    if (ov) atomicAdd(overflow_flag, 1ull);
+    traverse_sel<WIDTH>(S, sray, 0.001f, tmax, origin_prim, h);
     if (h.prim != PRIM_NONE) return v3(0, 0, 0);
     // Le * p_w / p_light, times the balance-heuristic weight p_light / (p_light + p_w)
     float weight = density / (light_density(S, r2, cos_y) + density);
@@ -931,8 +965,8 @@ __device__ __noinline__ V3 nee_direct(const DevScene& S, V3 p, V3 n, bool isotro
 // Camera.txt:240-272 with the one thing the reference leaves out: a shadow ray per light
 // (RT_FLAG_SHADOWED_POINT_LIGHTS, opt-in -- it changes the image on purpose: the reference's
 // point lights shine through everything).  Media on the way attenuate the light as well.
-__device__ __noinline__ V3 point_lighting_shadowed(const DevScene& S, V3 p, V3 normal, uint32_t origin_prim, float time,
-                                                   unsigned long long* overflow_flag) {
+template <int WIDTH>
+__device__ __noinline__ V3 point_lighting_shadowed(const DevScene& S, V3 p, V3 normal, uint32_t origin_prim, float time) {
     V3 result = v3(0, 0, 0);
     for (int i = 0; i < S.n_lights; i++) {
         const DevLight& l = S.lights[i];
@@ -947,9 +981,7 @@ __device__ __noinline__ V3 point_lighting_shadowed(const DevScene& S, V3 p, V3 n
         sray.d = ld;
         sray.time = time;
         Hit h;
-        int ov = 0;
-        traverse<false>(S, sray, 0.001f, dist, origin_prim, h, nullptr, &ov);
-        if (ov) atomicAdd(overflow_flag, 1ull);
+        traverse_sel<WIDTH>(S, sray, 0.001f, dist, origin_prim, h);
         if (h.prim != PRIM_NONE) continue;
         const float tm = S.n_media > 0 ? media_transmittance(S, sray, 0.001f, dist) : 1.0f;
         // the same arithmetic as point_lighting, so that an unoccluded light gives the same bits

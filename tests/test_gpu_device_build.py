@@ -114,7 +114,7 @@ def test_coincident_primitives_do_not_break_the_radix_tree(built):
     texs[0].type = 0
     texs[0].color[:] = [0.5, 0.5, 0.5]
     d = capi.rt_scene_desc()
-    d.struct_size, d.abi_version = C.sizeof(d), 2
+    d.struct_size, d.abi_version = C.sizeof(d), capi.RT_B200_ABI_VERSION
     d.world, d.n_world = refs, n
     d.spheres, d.n_spheres = sph, n
     d.materials, d.n_materials = mats, 1

@@ -44,7 +44,7 @@ def scene_desc(tris: np.ndarray):
     keep = {}
     d = capi.rt_scene_desc()
     d.struct_size = C.sizeof(d)
-    d.abi_version = 2
+    d.abi_version = capi.RT_B200_ABI_VERSION
     n = len(tris)
     refs = np.zeros(n + 1, dtype=REF)
     refs["type"][:n] = 2
