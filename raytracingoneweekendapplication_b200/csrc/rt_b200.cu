@@ -98,6 +98,9 @@ constexpr float kSampleClamp = 1048576.0f;   // 2^20: keeps 2^16 saturated sampl
 #ifndef RT_WIDE_MIN_BLOCKS
 #define RT_WIDE_MIN_BLOCKS RT_MIN_BLOCKS  // blocks per SM the wide instances are compiled for (register budget)
 #endif
+#ifndef RT_SMEM_STACK
+#define RT_SMEM_STACK 0  // binary kernel: this many traversal-stack entries per lane live in shared memory ([entry][thread]), the rest in local memory
+#endif
 #ifndef RT_V2_THREADS
 #define RT_V2_THREADS 256  // threads per block of render_kernel_v2 (tuning experiments: 224 x 3 trades warps for registers)
 #endif
@@ -146,10 +149,12 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
     uint32_t bounce = 0, origin_prim = PRIM_NONE;
     float nee_pdf = 0.0f;  // NEE: > 0 when the previous vertex sampled the listed emitters directly: the density of the direction it scattered into
     typename TravSel<WIDTH>::Trav tr;
-    StackEntry stack_mem[WIDTH == 2 ? STACK_SIZE : 1];
+    StackEntry stack_mem[WIDTH == 2 ? STACK_SIZE - RT_SMEM_STACK : 1];
     extern __shared__ uint2 wide_stack_mem[];
     auto stack = [&]() {
-        if constexpr (WIDTH == 2) return &stack_mem[0];
+        if constexpr (WIDTH == 2 && RT_SMEM_STACK == 0) return &stack_mem[0];
+        else if constexpr (WIDTH == 2)
+            return HybridStack<RT_SMEM_STACK, RT_V2_THREADS>{(uint32_t)__cvta_generic_to_shared(wide_stack_mem) + threadIdx.x * 8u, &stack_mem[0]};
         else return SmemStack<RT_V2_THREADS>::make(wide_stack_mem);
     }();
     tr.clear();
@@ -1405,14 +1410,14 @@ static RenderKernel v2_kernel(int variant, int width) {
     return width == 8 ? v2_instance<8>(variant) : (width == 4 ? v2_instance<4>(variant) : v2_instance<2>(variant));
 }
 // dynamic shared memory of a wide instance: the traversal stacks, [entry][thread]
-static size_t v2_smem(const rt_ctx* ctx, int width) { return width <= 2 ? 0 : (size_t)std::max(ctx->wide_depth, 1) * RT_V2_THREADS * sizeof(uint2); }
+static size_t v2_smem(const rt_ctx* ctx, int width) { return width <= 2 ? (size_t)RT_SMEM_STACK * RT_V2_THREADS * 8 : (size_t)std::max(ctx->wide_depth, 1) * RT_V2_THREADS * sizeof(uint2); }
 
 // blocks per SM the kernel instance runs with (the grid is persistent: SMs x this)
 static int v2_blocks_per_sm(rt_ctx* ctx, int variant, int width, int* out) {
     width = v2_effective_width(variant, width);
     RenderKernel k = v2_kernel(variant, width);
     const size_t smem = v2_smem(ctx, width);
-    if (width != 2) {
+    if (smem) {
         // carve out what RT_MIN_BLOCKS blocks need (plus the 1 KB the system reserves per block), the rest stays L1
         const int pct = (int)std::min<size_t>(100, (100 * RT_WIDE_MIN_BLOCKS * (smem + 1024) + 233471) / 233472);
         CU(ctx, cudaFuncSetAttribute((const void*)k, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
@@ -1487,8 +1492,14 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
     }
     const bool stats = (p->flags & RT_FLAG_STATS) != 0;
     int bps = ctx->blocks_per_sm[stats ? 1 : 0];
-    if (ctx->kernel_version == 2 && ctx->scene.wide_width && !(p->flags & (RT_FLAG_NEE | RT_FLAG_SHADOWED_POINT_LIGHTS))) {
-        rc = v2_blocks_per_sm(ctx, stats ? 2 : 0, ctx->scene.wide_width, &bps);
+    // which instance of render_kernel_v2 runs: LITE = no triangles, no point lights, no defocus blur in this scene (see hit_prim)
+    const bool lite = ctx->scene_lite && !getenv("RT_B200_NO_LITE");
+    const bool want_nee = (p->flags & RT_FLAG_NEE) != 0 && ctx->scene.n_nee_lights > 0;
+    const bool want_shadow = (p->flags & RT_FLAG_SHADOWED_POINT_LIGHTS) != 0 && ctx->scene.n_lights > 0;
+    const int variant = (want_nee || want_shadow) ? (lite ? 3 : 4) : (stats ? 2 : (lite ? 1 : 0));
+    const int width = ctx->scene.wide_width ? ctx->scene.wide_width : 2;
+    if (ctx->kernel_version == 2) {
+        rc = v2_blocks_per_sm(ctx, variant, width, &bps);
         if (rc != RT_OK) return rc;
     }
     const int grid = ctx->sm_count * (bps > 0 ? bps : 1);
@@ -1532,13 +1543,9 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
         } else
 #endif
         {
-            // LITE: no triangles, no point lights, no defocus blur in this scene (see hit_prim)
-            const bool lite = ctx->scene_lite && !getenv("RT_B200_NO_LITE");
-            A.nee_emitters = (p->flags & RT_FLAG_NEE) != 0 && ctx->scene.n_nee_lights > 0;
-            A.shadow_point_lights = (p->flags & RT_FLAG_SHADOWED_POINT_LIGHTS) != 0 && ctx->scene.n_lights > 0;
-            const bool nee = A.nee_emitters || A.shadow_point_lights;
-            const int variant = nee ? (lite ? 3 : 4) : (stats ? 2 : (lite ? 1 : 0));
-            rc = launch_v2(ctx, variant, ctx->scene.wide_width ? ctx->scene.wide_width : 2, grid, A, stream);
+            A.nee_emitters = want_nee;
+            A.shadow_point_lights = want_shadow;
+            rc = launch_v2(ctx, variant, width, grid, A, stream);
             if (rc != RT_OK) return rc;
         }
         CU(ctx, cudaGetLastError());

@@ -357,6 +357,32 @@ __device__ __forceinline__ StackEntry pack_entry(int link, float t) {
     return ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)link;
 }
 
+// Where a lane's stack lives.  A plain pointer = a local-memory array (every lane's entry at its own
+// depth is its own 32-byte sector: ncu measured 1.4-1.9 of 32 bytes used per sector).  HybridStack =
+// the first K entries in shared memory laid out [entry][thread] (the 32 lanes of a warp always hit 32
+// different banks, whatever depth each is at), deeper entries in the local array.
+__device__ __forceinline__ StackEntry stack_ld(const StackEntry* s, int i) { return s[i]; }
+__device__ __forceinline__ void stack_st(StackEntry* s, int i, StackEntry v) { s[i] = v; }
+template <int K, int STRIDE>
+struct HybridStack {
+    uint32_t addr;      // shared-window address of this thread's column
+    StackEntry* local;  // entries K and up
+};
+template <int K, int STRIDE>
+__device__ __forceinline__ StackEntry stack_ld(const HybridStack<K, STRIDE>& s, int i) {
+    if (i < K) {
+        StackEntry v;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(s.addr + (uint32_t)i * (STRIDE * 8u)));
+        return v;
+    }
+    return s.local[i - K];
+}
+template <int K, int STRIDE>
+__device__ __forceinline__ void stack_st(const HybridStack<K, STRIDE>& s, int i, StackEntry v) {
+    if (i < K) asm volatile("st.shared.u64 [%0], %1;" ::"r"(s.addr + (uint32_t)i * (STRIDE * 8u)), "l"(v) : "memory");
+    else s.local[i - K] = v;
+}
+
 struct Trav {
     Hit hit;
     int cur;  // >= 0 interior node, < 0 leaf, LINK_DONE finished (also < 0)
@@ -375,11 +401,12 @@ struct Trav {
     __device__ __forceinline__ bool wants_node() const { return cur >= 0; }
 
     // pop, skipping subtrees that start beyond the closest hit so far
-    __device__ __forceinline__ void pop(const StackEntry* stack) {
+    template <class Stack>
+    __device__ __forceinline__ void pop(const Stack& stack) {
         cur = LINK_DONE;
         while (sp > 0) {
             sp--;
-            const StackEntry e = stack[sp];
+            const StackEntry e = stack_ld(stack, sp);
             if (__uint_as_float((unsigned)(e >> 32)) <= hit.t) {
                 cur = (int)(unsigned)e;
                 break;
@@ -390,8 +417,8 @@ struct Trav {
     // One 64-byte node = two child boxes (aabb.h:61-85 twice).  The choice of the next link is
     // select-based: the four outcomes (both / left / right / none) share one instruction stream,
     // the push is a predicated store, and only the (rare) "none" case branches into pop().
-    template <bool STATS>
-    __device__ __forceinline__ void interior(const DevScene& S, const RayConst& rc, float tmin, StackEntry* stack, Stats* st,
+    template <bool STATS, class Stack>
+    __device__ __forceinline__ void interior(const DevScene& S, const RayConst& rc, float tmin, const Stack& stack, Stats* st,
                                              int* overflow) {
         const float4* n = S.nodes + 4 * (size_t)cur;
         float4 a = ldg4(n), b = ldg4(n + 1), c = ldg4(n + 2), e = ldg4(n + 3);
@@ -417,29 +444,29 @@ struct Trav {
             // no bounds check here: a ray's stack never holds more entries than the tree has levels, and
             // rt_upload_scene refuses (host path) or rebuilds on the host (device path) a tree with
             // STACK_SIZE levels or more.  The masked index + overflow flag this replaces cost 2.5 % on C5.
-            stack[sp] = pack_entry(far_l, far_t);
+            stack_st(stack, sp, pack_entry(far_l, far_t));
             sp++;
         }
         if (hl || hr) cur = near_l;
         else pop(stack);
     }
 
-    template <bool STATS, bool LITE = false>
+    template <bool STATS, bool LITE = false, class Stack>
     __device__ __forceinline__ void leaf(const DevScene& S, const Ray& ray, const RayConst& rc, float tmin, uint32_t origin_prim,
-                                         const StackEntry* stack, Stats* st) {
+                                         const Stack& stack, Stats* st) {
         uint32_t v = ~(uint32_t)cur;
         uint32_t type = v >> 28, cnt = ((v >> 25) & 7u) + 1u, first = v & 0x1ffffffu;
         for (uint32_t i = 0; i < cnt; i++) hit_prim<STATS, LITE>(S, type, first + i, ray, rc.inv_a, tmin, origin_prim, hit, st);
         pop(stack);
     }
 
-    template <bool STATS>
-    __device__ __forceinline__ void node_step(const DevScene& S, const Ray&, const RayConst& rc, float tmin, StackEntry* stack, Stats* st) {
+    template <bool STATS, class Stack>
+    __device__ __forceinline__ void node_step(const DevScene& S, const Ray&, const RayConst& rc, float tmin, const Stack& stack, Stats* st) {
         interior<STATS>(S, rc, tmin, stack, st, nullptr);
     }
-    template <bool STATS, bool LITE>
+    template <bool STATS, bool LITE, class Stack>
     __device__ __forceinline__ void leaf_step(const DevScene& S, const Ray& ray, const RayConst& rc, float tmin, uint32_t origin_prim,
-                                              const StackEntry* stack, Stats* st) {
+                                              const Stack& stack, Stats* st) {
         leaf<STATS, LITE>(S, ray, rc, tmin, origin_prim, stack, st);
     }
 };
@@ -453,9 +480,10 @@ __device__ __forceinline__ void traverse(const DevScene& S, const Ray& ray, floa
     Trav tr;
     StackEntry stack[STACK_SIZE];
     tr.init(S, tmax);
+    StackEntry* const sp_ = stack;
     while (!tr.done()) {
-        if (tr.cur >= 0) tr.interior<STATS>(S, rc, tmin, stack, st, overflow);
-        else tr.leaf<STATS>(S, ray, rc, tmin, origin_prim, stack, st);
+        if (tr.cur >= 0) tr.interior<STATS>(S, rc, tmin, sp_, st, overflow);
+        else tr.leaf<STATS>(S, ray, rc, tmin, origin_prim, sp_, st);
     }
     hit = tr.hit;
 }
