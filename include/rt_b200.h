@@ -331,8 +331,12 @@ int rt_download(rt_ctx* ctx, int32_t total_spp, float* rgb_linear, uint8_t* rgb8
 
 /* Deterministic primary-hit AOV for parity tests: casts the pixel-centre ray
  * ray(center, pixel00 + i*du + j*dv - center, time 0) over (0.001, inf) through
- * the same traversal/intersection code as rt_render.  Media are skipped
- * (stochastic).  prim_id = -1 on a miss.  Any output may be NULL. */
+ * the same traversal/intersection code as rt_render, which decides WHICH primitive
+ * is hit; t, point, normal and uv of that hit are then evaluated in double from the
+ * double-precision ray (the reference's own formulas: sphere.h:33-58, quad.h:30-47,
+ * triangle.h:67-110) and rounded to float once, so they can be held to 1e-5 against
+ * the reference.  rt_probe_hit reports the FP32 completion the render kernels use.
+ * Media are skipped (stochastic).  prim_id = -1 on a miss.  Any output may be NULL. */
 int rt_render_aov(rt_ctx* ctx, int32_t width, int32_t height,
                   int32_t* prim_id, float* t, float* normal /* 3 per pixel */,
                   float* point /* 3 per pixel */, float* uv /* 2 per pixel */);

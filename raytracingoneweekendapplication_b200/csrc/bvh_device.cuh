@@ -603,7 +603,10 @@ inline cudaError_t build_on_device(const rt_scene_desc* sc, unsigned char* scrat
             };
             for (rtbvh::Node& nd : top.nodes) { nd.llink = relink(nd.llink); nd.rlink = relink(nd.rlink); }
             if (top.root >= 0 && !top.nodes.empty()) {
-                if ((e = cudaMemcpy(T.nodes + 4 * (size_t)base, top.nodes.data(), top.nodes.size() * sizeof(rtbvh::Node), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+                // on `stream` and waited for: a plain cudaMemcpy from pageable memory returns once the data is staged, and
+                // the render kernels run on a non-blocking stream that the legacy stream does not order against
+                if ((e = cudaMemcpyAsync(T.nodes + 4 * (size_t)base, top.nodes.data(), top.nodes.size() * sizeof(rtbvh::Node), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+                if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
                 out.root = top.root + base;
                 out.top_nodes = (unsigned)top.nodes.size();
                 out.depth = top.depth + tallest + rebuilt_tallest;

@@ -374,14 +374,26 @@ __device__ __forceinline__ void traverse_uploaded(const DevScene& S, const Ray& 
     else traverse_sel<2>(S, ray, tmin, tmax, PRIM_NONE, hit);
 }
 
-__global__ void aov_kernel(const __grid_constant__ DevScene S, int width, int height, int* __restrict__ prim_id,
-                           float* __restrict__ t_out, float* __restrict__ normal, float* __restrict__ point,
-                           float* __restrict__ uv, unsigned long long* counters) {
+// Camera.txt:136-168 in double: the pixel-centre ray of pixel (i, j) is center + t * (dir00 + i du + j dv)
+struct CameraD {
+    double center[3], dir00[3], du[3], dv[3];
+};
+
+__global__ void aov_kernel(const __grid_constant__ DevScene S, const __grid_constant__ CameraD C, int width, int height,
+                           int* __restrict__ prim_id, float* __restrict__ t_out, float* __restrict__ normal, float* __restrict__ point,
+                           float* __restrict__ uv) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= width || j >= height) return;
+    // the ray in double (what the reference casts), rounded once for the FP32 traversal
+    RayD rd;
+    for (int k = 0; k < 3; k++) {
+        rd.o[k] = C.center[k];
+        rd.d[k] = C.dir00[k] + (double)i * C.du[k] + (double)j * C.dv[k];
+    }
+    rd.time = 0.0;
     Ray ray;
-    ray.o = v3(S.center);
-    ray.d = fma3((float)i, v3(S.du), fma3((float)j, v3(S.dv), v3(S.dir00)));
+    ray.o = v3((float)rd.o[0], (float)rd.o[1], (float)rd.o[2]);
+    ray.d = v3((float)rd.d[0], (float)rd.d[1], (float)rd.d[2]);
     ray.time = 0.0f;
     Hit hit;
     traverse_uploaded(S, ray, 0.001f, __int_as_float(0x7f800000), hit);
@@ -392,7 +404,7 @@ __global__ void aov_kernel(const __grid_constant__ DevScene S, int width, int he
     sf.u = sf.v = 0;
     float t = 0.0f;
     if (hit.prim != PRIM_NONE) {
-        complete_hit(S, ray, hit, sf, true);
+        complete_hit_fp64(S, rd, hit, sf);
         t = sf.t;
     }
     if (prim_id) prim_id[px] = sf.prim_id;
@@ -454,8 +466,7 @@ __global__ void probe_scatter_kernel(const __grid_constant__ DevScene S, int mat
 }
 
 __global__ void probe_hit_kernel(const __grid_constant__ DevScene S, int n, const float* __restrict__ rays, int* __restrict__ prim_id,
-                                 float* __restrict__ t_out, float* __restrict__ normal, float* __restrict__ uv,
-                                 unsigned long long* counters) {
+                                 float* __restrict__ t_out, float* __restrict__ normal, float* __restrict__ uv) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* r = rays + 9 * (size_t)i;
@@ -468,7 +479,7 @@ __global__ void probe_hit_kernel(const __grid_constant__ DevScene S, int n, cons
     sf.normal = v3(0, 0, 0);
     sf.u = sf.v = 0;
     sf.t = 0.0f;
-    if (hit.prim != PRIM_NONE) complete_hit(S, ray, hit, sf, true);
+    if (hit.prim != PRIM_NONE) complete_hit(S, ray, hit, sf, true);  // exactly what the render kernels compute (FP32, FP64 sphere refinement)
     if (prim_id) prim_id[i] = sf.prim_id;
     if (t_out) t_out[i] = sf.t;
     if (normal) { normal[3 * i] = sf.normal.x; normal[3 * i + 1] = sf.normal.y; normal[3 * i + 2] = sf.normal.z; }
@@ -522,6 +533,7 @@ struct rt_ctx {
     Stats* dstats = nullptr;
     rt_stats stats{};
     int cam_w = 0, cam_h = 0;  // frame the device camera block was computed for
+    CameraD camera_d{};        // the same camera in double (deterministic pixel-centre rays of the AOV)
     int sm_count = 0;
     int kernel_version = 2;  // 2 = render_kernel_v2; with -DRT_B200_ALT_KERNELS RT_B200_KERNEL=v1 | v3 | wf select the measured alternatives
 #ifdef RT_B200_ALT_KERNELS
@@ -840,6 +852,11 @@ static void setup_camera(rt_ctx* ctx, int width, int height) {
     put(S.disk_v, disk_v);
     put(S.background, d3(c.background));
     S.defocus = c.defocus_angle > 0 ? 1 : 0;
+    auto putd = [](double* dst, D3 s) { dst[0] = s.x; dst[1] = s.y; dst[2] = s.z; };
+    putd(ctx->camera_d.center, lookfrom);
+    putd(ctx->camera_d.dir00, dir00);
+    putd(ctx->camera_d.du, du);
+    putd(ctx->camera_d.dv, dv);
     ctx->cam_w = width;
     ctx->cam_h = height;
 }
@@ -1309,7 +1326,11 @@ extern "C" int rt_accum_upload(rt_ctx* ctx, const uint64_t* host, size_t bytes, 
     ctx->pending_async = false;
     int rc = ensure_accum(ctx, width, height);
     if (rc != RT_OK) return rc;
-    CU(ctx, cudaMemcpy(ctx->accum, host, need, cudaMemcpyHostToDevice));
+    // on the context's stream (cudaMemcpy from pageable memory returns once the data is STAGED; the DMA itself is
+    // ordered only against the legacy stream, and ctx->stream is non-blocking: a render enqueued right after could
+    // start before the sums have landed)
+    CU(ctx, cudaMemcpyAsync(ctx->accum, host, need, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     return RT_OK;
 }
 
@@ -1653,7 +1674,7 @@ extern "C" int rt_render_aov(rt_ctx* ctx, int32_t width, int32_t height, int32_t
     if (e == cudaSuccess) e = cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream);
     if (e == cudaSuccess) {
         dim3 block(8, 8), grid((width + 7) / 8, (height + 7) / 8);
-        aov_kernel<<<grid, block, 0, ctx->stream>>>(ctx->scene, width, height, d_id, d_t, d_n, d_p, d_uv, ctx->counters);
+        aov_kernel<<<grid, block, 0, ctx->stream>>>(ctx->scene, ctx->camera_d, width, height, d_id, d_t, d_n, d_p, d_uv);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -1718,7 +1739,9 @@ static int run_probe(rt_ctx* ctx, const char* name, const std::vector<std::pair<
     cudaError_t e = cudaSuccess;
     for (size_t i = 0; i < inputs.size() && e == cudaSuccess; i++) {
         e = cudaMalloc(&din[i], std::max<size_t>(inputs[i].second, 16));
-        if (e == cudaSuccess && inputs[i].second) e = cudaMemcpy(din[i], inputs[i].first, inputs[i].second, cudaMemcpyHostToDevice);
+        // stream-ordered with the probe kernel (a plain cudaMemcpy from pageable memory only guarantees staging:
+        // the kernel on the non-blocking ctx->stream could read the buffer before the DMA lands)
+        if (e == cudaSuccess && inputs[i].second) e = cudaMemcpyAsync(din[i], inputs[i].first, inputs[i].second, cudaMemcpyHostToDevice, ctx->stream);
     }
     for (size_t i = 0; i < outputs.size() && e == cudaSuccess; i++)
         if (outputs[i].first) e = cudaMalloc(&dout[i], std::max<size_t>(outputs[i].second, 16));
@@ -1765,8 +1788,7 @@ extern "C" int rt_probe_hit(rt_ctx* ctx, int32_t n, const float* rays, int32_t* 
                        {{prim_id, (size_t)n * 4}, {t, (size_t)n * 4}, {normal, (size_t)n * 12}, {uv, (size_t)n * 8}},
                        [&](std::vector<void*>& in, std::vector<void*>& out) {
                            probe_hit_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, n, (const float*)in[0], (int*)out[0],
-                                                                                       (float*)out[1], (float*)out[2], (float*)out[3],
-                                                                                       ctx->counters);
+                                                                                       (float*)out[1], (float*)out[2], (float*)out[3]);
                        });
     return rc;
 }

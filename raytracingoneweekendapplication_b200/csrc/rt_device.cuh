@@ -11,7 +11,8 @@
 //   msph       moving spheres, 32 B  {c0.xyz, r} {cvec.xyz, 0}
 //   quad       48 B  {n.xyz, D} {A.xyz, a0} {B.xyz, b0}   alpha = A.P - a0, beta = B.P - b0
 //   tri        48 B  {p0.xyz, 0} {e1.xyz, 0} {e2.xyz, 0}
-//   *_d        FP64 copies used by the near-surface / near-edge refinement paths
+//   *_d        FP64 copies: sphere paths of the render kernels (near-surface roots, refinement of the
+//              accepted hit) and complete_hit_fp64 of the deterministic rays (AOV, probes)
 //   *_sh       shading records fetched once per accepted hit
 // Typed arrays are stored in BVH leaf order, so a leaf's primitives are contiguous and
 // there is no index indirection.  Media boundaries live at the tail of the same arrays.
@@ -756,6 +757,94 @@ __device__ __forceinline__ void complete_hit(const DevScene& S, const Ray& ray, 
     }
     sf.front = dot(ray.d, outward) < 0.0f;  // hittable.h:22-25
     sf.normal = sf.front ? outward : -outward;
+}
+
+// The accepted hit of a DETERMINISTIC ray (primary-hit AOV, probe rays) completed in double from the
+// double-precision ray: the FP32 traversal decides WHICH primitive (and which sphere root), this pass
+// restates the reference's own arithmetic for t, p, normal and uv (sphere.h:33-58, quad.h:30-47 with the
+// planar coordinates as dot products, triangle.h:67-110) on the FP64 copies of the records, so that the
+// parity gate compares values good to FP32 rounding of the RESULT (north_star: t and normal within 1e-5).
+// Out of line; the render kernels never call it (their rays are FP32 by construction).
+struct RayD {
+    double o[3], d[3], time;
+};
+__device__ __noinline__ void complete_hit_fp64(const DevScene& S, const RayD& r, const Hit& hit, Surface& sf) {
+    const uint32_t type = hit.prim >> 28, idx = hit.prim & 0x0fffffffu;
+    const double ox = r.o[0], oy = r.o[1], oz = r.o[2], dx = r.d[0], dy = r.d[1], dz = r.d[2];
+    double t, nx, ny, nz;
+    sf.nee_light = 0;
+    sf.u = sf.v = 0.0f;
+    if (type == PT_SPHERE || type == PT_MSPHERE) {
+        double cx, cy, cz, rr;
+        int4 sh;
+        if (type == PT_SPHERE) {
+            const double* cd = S.sph_d + 4 * (size_t)idx;
+            cx = cd[0]; cy = cd[1]; cz = cd[2]; rr = cd[3];
+            sh = __ldg(S.sph_sh + idx);
+        } else {
+            const double* cd = S.msph_d + 8 * (size_t)idx;
+            cx = cd[0] + r.time * cd[4]; cy = cd[1] + r.time * cd[5]; cz = cd[2] + r.time * cd[6];
+            rr = cd[3];
+            sh = __ldg(S.msph_sh + idx);
+        }
+        const double qx = cx - ox, qy = cy - oy, qz = cz - oz;
+        const double a = dx * dx + dy * dy + dz * dz;
+        const double hh = dx * qx + dy * qy + dz * qz;
+        const double cc = qx * qx + qy * qy + qz * qz - rr * rr;
+        const double sq = sqrt(fmax(hh * hh - a * cc, 0.0));
+        const double ta = (hh - sq) / a, tb = (hh + sq) / a;
+        t = fabs(ta - (double)hit.t) <= fabs(tb - (double)hit.t) ? ta : tb;
+        const double px = ox + t * dx, py = oy + t * dy, pz = oz + t * dz;
+        nx = (px - cx) / rr; ny = (py - cy) / rr; nz = (pz - cz) / rr;  // sphere.h:52
+        sf.material = sh.x;
+        sf.prim_id = sh.z;
+        double ux = nx, uy = ny, uz = nz;
+        if (sh.y >= 0) {  // back to object space: R^T n
+            const float* R = S.xrot + 9 * (size_t)sh.y;
+            ux = R[0] * nx + R[3] * ny + R[6] * nz;
+            uy = R[1] * nx + R[4] * ny + R[7] * nz;
+            uz = R[2] * nx + R[5] * ny + R[8] * nz;
+        }
+        const double pi = 3.1415926535897932385;  // sphere.h:67-73
+        sf.u = (float)((atan2(-uz, ux) + pi) / (2.0 * pi));
+        sf.v = (float)(acos(fmin(fmax(-uy, -1.0), 1.0)) / pi);
+    } else if (type == PT_QUAD) {
+        const double* q = S.quad_d + 12 * (size_t)idx;
+        nx = q[0]; ny = q[1]; nz = q[2];
+        t = (q[3] - (nx * ox + ny * oy + nz * oz)) / (nx * dx + ny * dy + nz * dz);
+        const double px = ox + t * dx, py = oy + t * dy, pz = oz + t * dz;
+        sf.u = (float)(q[4] * px + q[5] * py + q[6] * pz - q[7]);
+        sf.v = (float)(q[8] * px + q[9] * py + q[10] * pz - q[11]);
+        const int4 sh = __ldg(S.quad_sh + idx);
+        sf.material = sh.x;
+        sf.prim_id = sh.z;
+        sf.nee_light = sh.w;
+    } else {
+        const double* td = S.tri_d + 9 * (size_t)idx;
+        const double e1x = td[3], e1y = td[4], e1z = td[5], e2x = td[6], e2y = td[7], e2z = td[8];
+        const double pvx = dy * e2z - dz * e2y, pvy = dz * e2x - dx * e2z, pvz = dx * e2y - dy * e2x;
+        const double inv = 1.0 / (e1x * pvx + e1y * pvy + e1z * pvz);
+        const double tx = ox - td[0], ty = oy - td[1], tz = oz - td[2];
+        const double bu = (tx * pvx + ty * pvy + tz * pvz) * inv;
+        const double qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+        const double bv = (dx * qx + dy * qy + dz * qz) * inv;
+        t = (e2x * qx + e2y * qy + e2z * qz) * inv;
+        const float4* ts = S.tri_sh + 3 * (size_t)idx;
+        const float4 a = ldg4(ts), b = ldg4(ts + 1), c = ldg4(ts + 2);
+        // the unit normal from the FP64 edges (triangle.h:21-22)
+        const double cxn = e1y * e2z - e1z * e2y, cyn = e1z * e2x - e1x * e2z, czn = e1x * e2y - e1y * e2x;
+        const double il = 1.0 / sqrt(cxn * cxn + cyn * cyn + czn * czn);
+        nx = cxn * il; ny = cyn * il; nz = czn * il;
+        sf.material = __float_as_int(a.w);
+        sf.prim_id = __float_as_int(c.z);
+        const double alpha = 1.0 - bu - bv;  // triangle.h:96-104
+        sf.u = (float)(alpha * b.x + bu * b.z + bv * c.x);
+        sf.v = (float)(alpha * b.y + bu * b.w + bv * c.y);
+    }
+    sf.t = (float)t;
+    sf.p = v3((float)(ox + t * dx), (float)(oy + t * dy), (float)(oz + t * dz));
+    sf.front = dx * nx + dy * ny + dz * nz < 0.0;  // hittable.h:22-25
+    sf.normal = sf.front ? v3((float)nx, (float)ny, (float)nz) : v3((float)-nx, (float)-ny, (float)-nz);
 }
 
 // vec3.h:107-115: the `1e-160 < lensq <= 1` test is always true, so this is

@@ -60,6 +60,29 @@ def test_primary_hits_and_images_match_the_host_path(scene_of, name):
     assert same_px.mean() >= (0.99 if tie.any() else 1.0), f"{name}: {(~same_px).sum()} pixels differ"
 
 
+@pytest.mark.parametrize("name", ["final", "mesh", "book1", "mixed"])
+def test_device_built_tree_against_the_reference_fixture(scene_of, name):
+    """The device-built tree checked DIRECTLY against the fixture dumped from the unmodified reference
+    (not only against the host-built tree): the gate of test_gpu_primary.py with set_bvh_builder('device')."""
+    import test_gpu_primary
+
+    sc = scene_of(name)
+    gold = helpers.golden("primary", name)
+    h, w = gold["ids"].shape
+    c = capi.Context(0)
+    try:
+        c.set_bvh_builder("device")
+        c.upload(sc)
+        st = c.stats()
+        assert st["bvh_on_device"] == 1 and 0 < st["bvh_depth"] < 62   # the depth the unchecked device stack relies on
+        aov = c.aov(w, h)
+    finally:
+        c.close()
+    r = helpers.compare_primary(gold, aov, helpers.flat_leaf_keys(sc.desc), helpers.undecidable_pixels(sc, w, h))
+    test_gpu_primary.record(f"device_built/{name}/{w}x{h}", r)
+    test_gpu_primary.check(r)
+
+
 def test_large_triangle_soup(built):
     import upload_scale
 

@@ -1,7 +1,14 @@
 """Parity gate (a): deterministic primary rays at pixel centres.  The device's hit primitive
 must equal the reference's on >= 99.99 % of pixels, with t and normal within 1e-5 relative
-(FP32 device vs the reference's double).  All calls go through the C ABI (rt_render_aov /
-rt_probe_hit)."""
+(FP32 device vs the reference's double), as north_star states it.  All calls go through the C ABI:
+rt_render_aov (FP32 traversal decides the primitive, the accepted hit is completed in double from
+the double-precision pixel-centre ray) is the gate; rt_probe_hit (the render kernels' own FP32
+completion) is held to the bounds FP32 can keep, stated in test_fp32_completion_bounds.
+Every comparison is also written to gpurun_out/parity_report.json (committed as
+profiles/r2_parity.json)."""
+import json
+import os
+
 import numpy as np
 import pytest
 
@@ -13,6 +20,15 @@ pytestmark = pytest.mark.gpu
 SCENES = ["book1", "cornell", "cornell_smoke", "mesh", "final", "quads", "emissive", "specular", "mixed", "kitchen_sink"]
 T_TOL = 1e-5   # relative, north_star
 N_TOL = 1e-5   # absolute on unit normals
+REPORT = {}
+
+
+def record(key, r):
+    REPORT[key] = {k: v for k, v in r.items() if k != "mismatch_pixels"}
+    out = os.path.join(helpers.ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_report.json"), "w") as f:
+        json.dump(REPORT, f, indent=1, sort_keys=True)
 
 
 def check(r):
@@ -20,11 +36,9 @@ def check(r):
     # helpers.undecidable_pixels; they must stay a sliver of the frame)
     assert r["id_match"] >= 0.9999, r
     assert r["undecidable"] <= 0.01 * r["pixels"], r
-    assert r["t_within_1e5"] >= 0.9999 and r["t_rel_max"] <= 10 * T_TOL, r
-    # normals: the accepted sphere hit is re-solved in FP64, so what remains is the FP32
-    # REPRESENTATION of the ray itself (1e-7 relative in the direction), which a sphere of
-    # radius r at distance s amplifies by s / (r cos(incidence)): > 1e-5 only at grazing hits
-    assert r["n_within_1e5"] >= 0.995 and r["n_err_max"] <= 2e-3, r
+    # t and normal within 1e-5 on >= 99.99 % of the pixels, and t nowhere worse
+    assert r["t_within_1e5"] >= 0.9999 and r["t_rel_max"] <= T_TOL, r
+    assert r["n_within_1e5"] >= 0.9999, r
 
 
 @pytest.mark.parametrize("name", SCENES)
@@ -35,8 +49,9 @@ def test_primary_hits_match_reference_fixture(ctx, scene_of, name):
     g = helpers.golden("primary", name)
     h, w = g["ids"].shape
     r = helpers.compare_primary(g, ctx.aov(w, h), helpers.flat_leaf_keys(sc.desc), helpers.undecidable_pixels(sc, w, h))
+    record(f"fixture/{name}/{w}x{h}", r)
     check(r)
-    assert r["uv_err_max"] <= 5e-4, r
+    assert r["uv_err_max"] <= 5e-6, r
 
 
 @pytest.mark.parametrize("name,w,h", [("book1", 400, 225), ("cornell", 600, 600), ("cornell_smoke", 600, 600),
@@ -52,7 +67,30 @@ def test_primary_hits_match_oracle_at_baseline_frames(ctx, scene_of, name, w, h)
     keys = helpers.flat_leaf_keys(sc.desc)
     gold = {"ids": o["prim_id"].reshape(h, w), "t": o["t"].reshape(h, w), "normal": o["normal"].reshape(h, w, 3),
             "uv": o["uv"].reshape(h, w, 2), "leaves": keys}
-    check(helpers.compare_primary(gold, ctx.aov(w, h), keys, helpers.undecidable_pixels(sc, w, h)))
+    r = helpers.compare_primary(gold, ctx.aov(w, h), keys, helpers.undecidable_pixels(sc, w, h))
+    record(f"baseline_frame/{name}/{w}x{h}", r)
+    check(r)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_fp32_completion_bounds(ctx, scene_of, name):
+    """The same pixel-centre rays, stored as FP32, through rt_probe_hit: the hit is completed by the code the
+    render kernels run (FP32; spheres re-solved in FP64 from the FP32 ray).  What FP32 keeps (measured:
+    profiles/r2_parity.json, keys fp32_completion/*): the same primitive, t within 1e-5 EVERYWHERE (worst 2.3e-6),
+    normals within 1e-5 on >= 99.9 % (worst scene 99.94 %, worst normal 8e-5) -- the rest is the FP32
+    REPRESENTATION of the ray (1e-7 relative in its direction), which a sphere of radius r at distance s amplifies
+    by s / (r cos(incidence)), i.e. only grazing hits of small far spheres."""
+    sc = scene_of(name)
+    ctx.upload(sc)
+    g = helpers.golden("primary", name)
+    h, w = g["ids"].shape
+    rays = helpers.camera_center_rays(sc.desc.camera, w, h)
+    dev = ctx.probe_hit(rays)
+    r = helpers.compare_primary(g, dev, helpers.flat_leaf_keys(sc.desc), helpers.undecidable_pixels(sc, w, h))
+    record(f"fp32_completion/{name}/{w}x{h}", r)
+    assert r["id_match"] >= 0.9999, r
+    assert r["t_within_1e5"] >= 0.9999 and r["t_rel_max"] <= T_TOL, r
+    assert r["n_within_1e5"] >= 0.999 and r["n_err_max"] <= 1e-3, r
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
