@@ -16,7 +16,9 @@
  *     last failure on a context is available from rt_last_error().
  *   - nothing throws across the boundary; there is no global state.
  *   - a context is driven by one host thread at a time; distinct contexts are
- *     independent (one context per GPU; one process per GPU under torchrun).
+ *     independent.  A context owns one GPU or several GPUs of one box (rt_create);
+ *     under torchrun every process creates a one-GPU context and shards the frame with
+ *     rt_render_params::shard_rank / shard_count.
  *   - all pointers passed IN are copied before the call returns (the caller keeps
  *     ownership and may free immediately); all pointers passed OUT are
  *     caller-allocated.
@@ -219,6 +221,12 @@ typedef enum rt_shard_mode {
                                  density of the reference's own direction sampler, so the CONVERGED image is the one
                                  the reference converges to; individual samples differ, noise is lower.  Ignored when
                                  the scene has no quad emitter. */
+#define RT_FLAG_COMPACT_TILES 32u /* tile-sharded render (shard_mode RT_SHARD_TILES, tile_size a power of two) into a COMPACT
+                                 accumulation buffer that holds only this shard's tiles: tile t of the frame is local tile
+                                 t / shard_count of shard t mod shard_count, stored as tile_size x tile_size slots --
+                                 1 / shard_count of the frame instead of all of it.  rt_resolve_tiles / rt_untile move and
+                                 reassemble such shards; rt_download and rt_accum_download still hand out the full frame
+                                 (this shard's tiles in place, zero elsewhere).  A multi-device context sets it itself. */
 #define RT_FLAG_SHADOWED_POINT_LIGHTS 16u /* opt-in: a shadow ray (and media transmittance) per point light in the
                                  term of Camera.txt:240-272.  The reference's point lights are unshadowed, so this
                                  changes the image on purpose. */
@@ -279,12 +287,20 @@ typedef struct rt_stats {
      * tree with 8-bit quantised child boxes (80 / 48 bytes per node); node count and levels of the wide tree */
     uint32_t bvh_width, wide_nodes, wide_depth, reserved2_;
     uint64_t empty_node_steps; /* node steps in which no child box was hit (RT_FLAG_STATS) */
+    /* multi-device contexts: devices of the context (counters above are summed over them, render_ms is the slowest
+     * device's) and how rt_download gathers their tiles on device 0: 0 single device, 1 peer copies, 2 NCCL send/recv */
+    uint32_t devices, gather_mode;
 } rt_stats;
 
-/* Create a context on CUDA device `device_ids[0]` (n_devices must be 1: this
- * library runs one context per GPU; multi-GPU frames are sharded with
- * rt_render_params::shard_rank/shard_count and summed with rt_accum_buffer). */
+/* Create a context on the CUDA devices device_ids[0 .. n_devices).  With n_devices > 1 the context
+ * replicates the scene on every device, rt_render gives tile t of the frame to device t mod n_devices
+ * (compact per-device tile buffers, all devices running concurrently) and rt_download gathers the resolved
+ * tiles on device_ids[0] over NVLink (NCCL send/recv when libnccl.so.2 loads, peer copies otherwise;
+ * RT_B200_GATHER=nccl|p2p forces one).  The image does not depend on n_devices, bit for bit.  Replaces the
+ * reference's row bands over CPU threads (Camera.txt:59-61, 96-100).  *out is set even on failure so that
+ * rt_last_error works; destroy it. */
 int rt_create(rt_ctx** out, const int* device_ids, int n_devices);
+int rt_device_count(const rt_ctx* ctx);
 void rt_destroy(rt_ctx* ctx);
 const char* rt_last_error(const rt_ctx* ctx);
 
@@ -348,7 +364,8 @@ int rt_render_aov(rt_ctx* ctx, int32_t width, int32_t height,
  * the device pointer (valid until the next rt_render with a different frame size,
  * rt_bind_accum or rt_destroy) so the caller can reduce it across GPUs with NCCL
  * (int64 SUM); rt_bind_accum makes the context render into a caller-owned device
- * buffer (e.g. a torch tensor) instead; NULL unbinds. */
+ * buffer (e.g. a torch tensor) instead; NULL unbinds.  Both are for single-device contexts and full
+ * (not compact) frames. */
 #define RT_ACCUM_FRAC_BITS 28
 int rt_accum_buffer(rt_ctx* ctx, void** device_ptr, size_t* bytes);
 int rt_bind_accum(rt_ctx* ctx, void* device_ptr, size_t bytes, int32_t width, int32_t height);
@@ -361,6 +378,19 @@ int rt_bind_accum(rt_ctx* ctx, void* device_ptr, size_t bytes, int32_t width, in
  * uninterrupted render of the same total. */
 int rt_accum_download(rt_ctx* ctx, uint64_t* host, size_t bytes);
 int rt_accum_upload(rt_ctx* ctx, const uint64_t* host, size_t bytes, int32_t width, int32_t height);
+
+/* Compact tile buffers across processes (one process per GPU, e.g. under torchrun; single-device contexts):
+ *   rt_shard_pixels   slots of the compact buffer of shard (rank, count): its tiles x tile_size^2 (edge tiles padded)
+ *   rt_resolve_tiles  the compact sums of the last RT_FLAG_COMPACT_TILES render -> averaged radiance (3 floats per slot)
+ *                     and / or RGB8 (3 bytes per slot, Camera.txt:77-89) in CALLER-OWNED DEVICE buffers of
+ *                     capacity_pixels slots each, ready for an NCCL gather by the caller
+ *   rt_untile         `shard_count` such buffers side by side on this context's device (shard r at
+ *                     dev_shards + r * shard_stride_bytes) -> the full row-major frame in host memory;
+ *                     bytes_per_pixel 3 (RGB8), 12 (float RGB) or 32 (raw sums) */
+size_t rt_shard_pixels(int32_t width, int32_t height, int32_t tile_size, int32_t shard_rank, int32_t shard_count);
+int rt_resolve_tiles(rt_ctx* ctx, int32_t total_spp, float* dev_rgb_linear, uint8_t* dev_rgb8, size_t capacity_pixels);
+int rt_untile(rt_ctx* ctx, const void* dev_shards, size_t shard_stride_bytes, int32_t bytes_per_pixel, int32_t shard_count,
+              int32_t width, int32_t height, int32_t tile_size, void* host_out);
 
 int rt_get_stats(rt_ctx* ctx, rt_stats* out);
 

@@ -22,7 +22,7 @@ RT_PRIM_SPHERE, RT_PRIM_QUAD, RT_PRIM_TRIANGLE = range(3)
  RT_MAT_SPECULAR) = range(7)
 RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_CHECKER_TRIANGLE, RT_TEX_IMAGE, RT_TEX_NOISE = range(5)
 RT_SHARD_AUTO, RT_SHARD_TILES, RT_SHARD_SAMPLES = range(3)
-RT_FLAG_ACCUMULATE, RT_FLAG_ASYNC, RT_FLAG_STATS, RT_FLAG_NEE, RT_FLAG_SHADOWED_POINT_LIGHTS = 1, 2, 4, 8, 16
+RT_FLAG_ACCUMULATE, RT_FLAG_ASYNC, RT_FLAG_STATS, RT_FLAG_NEE, RT_FLAG_SHADOWED_POINT_LIGHTS, RT_FLAG_COMPACT_TILES = 1, 2, 4, 8, 16, 32
 
 d3 = C.c_double * 3
 
@@ -123,6 +123,7 @@ class rt_stats(C.Structure):
         ("device_top_ms", C.c_double),
         ("bvh_width", C.c_uint32), ("wide_nodes", C.c_uint32), ("wide_depth", C.c_uint32), ("reserved2_", C.c_uint32),
         ("empty_node_steps", C.c_uint64),
+        ("devices", C.c_uint32), ("gather_mode", C.c_uint32),
     ]
 
     def as_dict(self) -> dict:
@@ -133,7 +134,7 @@ EXPORTED_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_upload_scene", "rt_render", "rt_sync", "rt_download", "rt_render_aov",
     "rt_accum_buffer", "rt_bind_accum", "rt_get_stats", "rt_measure_fp32_peak", "rt_probe_texture", "rt_probe_scatter",
     "rt_probe_hit", "rt_struct_size", "rt_accum_download", "rt_accum_upload", "rt_set_bvh_builder",
-    "rt_set_bvh_width",
+    "rt_set_bvh_width", "rt_device_count", "rt_shard_pixels", "rt_resolve_tiles", "rt_untile",
 ]
 
 ABI_STRUCTS = [rt_scene_desc, rt_render_params, rt_stats, rt_sphere, rt_quad, rt_triangle, rt_medium, rt_material, rt_texture,
@@ -184,6 +185,11 @@ def load() -> C.CDLL:
     lib.rt_get_stats.argtypes = [vp, C.POINTER(rt_stats)]
     lib.rt_set_bvh_builder.argtypes = [vp, i32]
     lib.rt_set_bvh_width.argtypes = [vp, i32]
+    lib.rt_device_count.argtypes = [vp]
+    lib.rt_shard_pixels.argtypes = [i32, i32, i32, i32, i32]
+    lib.rt_shard_pixels.restype = C.c_size_t
+    lib.rt_resolve_tiles.argtypes = [vp, i32, vp, vp, C.c_size_t]
+    lib.rt_untile.argtypes = [vp, vp, C.c_size_t, i32, i32, i32, i32, i32, vp]
     lib.rt_accum_download.argtypes = [vp, vp, C.c_size_t]
     lib.rt_accum_upload.argtypes = [vp, vp, C.c_size_t, i32, i32]
     lib.rt_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
@@ -293,13 +299,14 @@ def scene_names() -> list:
 
 
 class Context:
-    """One rt_ctx (one GPU)."""
+    """One rt_ctx: one GPU (device = an index) or several GPUs of this box (device = a list of indices)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
         self.lib = load()
         self._h = C.c_void_p()
-        dev = C.c_int32(device)
-        rc = self.lib.rt_create(C.byref(self._h), C.byref(dev), 1)
+        ids = [device] if isinstance(device, int) else list(device)
+        dev = (C.c_int32 * max(1, len(ids)))(*ids)
+        rc = self.lib.rt_create(C.byref(self._h), dev, len(ids))
         if rc != RT_OK:
             msg = self.lib.rt_last_error(self._h).decode() if self._h else "rt_create failed"
             if self._h:
@@ -333,14 +340,15 @@ class Context:
     def render(self, width: int, height: int, spp: int, max_depth: int = 50, seed: int = 1, spp_begin: int = 0,
                accumulate: bool = False, stats: bool = False, shard_rank: int = 0, shard_count: int = 1,
                shard_mode: int = RT_SHARD_AUTO, tile_size: int = 0, stream: Optional[int] = None, blocking: bool = True,
-               nee: bool = False, shadowed_point_lights: bool = False) -> None:
+               nee: bool = False, shadowed_point_lights: bool = False, compact: bool = False) -> None:
         p = rt_render_params()
         p.struct_size = C.sizeof(rt_render_params)
         p.width, p.height, p.samples_per_pixel, p.max_depth = width, height, spp, max_depth
         p.spp_begin, p.seed, p.tile_size = spp_begin, seed, tile_size
         p.shard_mode, p.shard_rank, p.shard_count = shard_mode, shard_rank, shard_count
         p.flags = ((RT_FLAG_ACCUMULATE if accumulate else 0) | (RT_FLAG_STATS if stats else 0) | (0 if blocking else RT_FLAG_ASYNC) |
-                   (RT_FLAG_NEE if nee else 0) | (RT_FLAG_SHADOWED_POINT_LIGHTS if shadowed_point_lights else 0))
+                   (RT_FLAG_NEE if nee else 0) | (RT_FLAG_SHADOWED_POINT_LIGHTS if shadowed_point_lights else 0) |
+                   (RT_FLAG_COMPACT_TILES if compact else 0))
         p.stream = stream
         self._check(self.lib.rt_render(self._h, C.byref(p)))
         self.width, self.height = width, height
@@ -366,6 +374,26 @@ class Context:
             "uv": np.empty((n, 2), dtype=np.float32),
         }
         self._check(self.lib.rt_render_aov(self._h, width, height, *[out[k].ctypes.data for k in ("prim_id", "t", "normal", "point", "uv")]))
+        return out
+
+    def device_count(self) -> int:
+        return self.lib.rt_device_count(self._h)
+
+    def resolve_tiles(self, total_spp: int, dev_rgb8: Optional[int], capacity_pixels: int, dev_linear: Optional[int] = None) -> None:
+        """The compact tiles of the last compact render -> RGB8 / float radiance in caller-owned DEVICE buffers."""
+        self._check(self.lib.rt_resolve_tiles(self._h, total_spp, dev_linear, dev_rgb8, capacity_pixels))
+
+    def untile(self, dev_shards: int, shard_stride_bytes: int, bytes_per_pixel: int, shard_count: int, width: int, height: int,
+               tile_size: int = 16) -> np.ndarray:
+        """`shard_count` compact buffers side by side on this context's device -> the full frame (host array)."""
+        if bytes_per_pixel == 3:
+            out = np.empty((height, width, 3), dtype=np.uint8)
+        elif bytes_per_pixel == 12:
+            out = np.empty((height, width, 3), dtype=np.float32)
+        else:
+            out = np.empty((height, width, 4), dtype=np.uint64)
+        self._check(self.lib.rt_untile(self._h, dev_shards, shard_stride_bytes, bytes_per_pixel, shard_count, width, height, tile_size,
+                                       out.ctypes.data))
         return out
 
     def accum_buffer(self):

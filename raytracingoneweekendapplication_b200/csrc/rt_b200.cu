@@ -56,6 +56,7 @@ struct RenderArgs {
     int blocks_per_tile_x, blocks_per_tile_y;  // 8x4 pixel blocks per tile
     unsigned long long n_items;
     uint32_t k0, k1;
+    int compact;             // RT_FLAG_COMPACT_TILES: `accum` holds only this shard's tiles, tile-major: slot = local_tile * tile_size^2 + y_in_tile * tile_size + x_in_tile
     int nee_emitters;        // NEE instance: sample the listed quad emitters (RT_FLAG_NEE)
     int shadow_point_lights; // NEE instance: shadow rays for the point lights (RT_FLAG_SHADOWED_POINT_LIGHTS)
 };
@@ -135,6 +136,10 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
     // warp-uniform pool of (pixel, sample) pairs
     unsigned pool_pos = 0, pool_size = 0;
     int blk_x0 = 0, blk_y0 = 0, seg_s0 = 0;
+    // compact tile buffers: where a lane's current sample goes.  One word of shared memory per lane, written
+    // when the sample starts and read when it ends -- no register is held across the whole path for it
+    __shared__ uint32_t lane_slot[RT_V2_THREADS];
+    unsigned slot_base = 0;
     bool exhausted = A.max_depth <= 0;  // ray_color(depth <= 0) is black before anything is traced
 
     int state = LANE_IDLE;
@@ -187,6 +192,8 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
                 seg_s0 = (int)seg * A.seg_len;
                 pool_size = 32u * (unsigned)min(A.seg_len, A.n_local_samples - seg_s0);
                 pool_pos = 0;
+                slot_base = (local_tile * (unsigned)A.tile_size + (in_tile / (unsigned)A.blocks_per_tile_x) * 4u) * (unsigned)A.tile_size +
+                            (in_tile % (unsigned)A.blocks_per_tile_x) * 8u;
             }
             const unsigned e = pool_pos + __popc(needy & lt_mask);
             if (state == LANE_IDLE && e < pool_size) {
@@ -194,6 +201,7 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
                 if (px < A.width && py < A.height) {
                     rng.pixel = (uint32_t)(py * A.width + px);
                     rng.sample = (uint32_t)(A.spp_begin + A.sample_offset + (seg_s0 + (int)(e >> 5)) * A.sample_stride);
+                    if (A.compact) lane_slot[threadIdx.x] = slot_base + ((e >> 3) & 3u) * (unsigned)A.tile_size + (e & 7u);
                     ray = camera_ray<LITE>(S, px, py, rng);
                     L = v3(0, 0, 0);
                     T = v3(1, 1, 1);
@@ -335,7 +343,7 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
                 }
             }
             if (done) {
-                unsigned long long* a = accum + 4ull * rng.pixel;
+                unsigned long long* a = accum + 4ull * (A.compact ? lane_slot[threadIdx.x] : rng.pixel);
                 if (isfinite(L.x) && isfinite(L.y) && isfinite(L.z)) {
                     atomicAdd(a + 0, __float2ull_rn(fminf(fmaxf(L.x, 0.0f), kSampleClamp) * kAccumScale));
                     atomicAdd(a + 1, __float2ull_rn(fminf(fmaxf(L.y, 0.0f), kSampleClamp) * kAccumScale));
@@ -505,7 +513,25 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
-struct rt_ctx {
+// Layout of an accumulation buffer.  Full: one 32-byte slot per pixel, row-major.  Compact
+// (RT_FLAG_COMPACT_TILES): only the tiles of one shard (tile t of the frame belongs to shard t mod count
+// and is its local tile t / count), each tile a tile_size x tile_size block of slots -- 1 / count of the
+// frame, which is what a GPU of a tile-sharded frame needs and what travels in the gather.
+struct AccumLayout {
+    int width = 0, height = 0;
+    bool compact = false;
+    int rank = 0, count = 1, tile = 16;
+    bool operator==(const AccumLayout& o) const {
+        return width == o.width && height == o.height && compact == o.compact && (!compact || (rank == o.rank && count == o.count && tile == o.tile));
+    }
+    size_t local_tiles() const {
+        const size_t tiles = (size_t)((width + tile - 1) / tile) * ((height + tile - 1) / tile);
+        return tiles > (size_t)rank ? (tiles - rank + count - 1) / count : 0;
+    }
+    size_t slots() const { return compact ? local_tiles() * tile * tile : (size_t)width * height; }
+};
+
+struct DevCtx {
     int device = 0;
     std::string error;
     cudaStream_t stream = nullptr;
@@ -526,9 +552,11 @@ struct rt_ctx {
     rt_camera camera{};
     // accumulation
     unsigned long long* accum = nullptr;
-    size_t accum_bytes = 0;
+    size_t accum_bytes = 0, accum_cap = 0;
     bool accum_external = false;
-    int acc_w = 0, acc_h = 0;
+    AccumLayout acc;                        // layout of `accum`
+    unsigned char* frame_scratch = nullptr;  // full-frame copies of compact data (checkpoints, single-shard downloads)
+    size_t frame_scratch_cap = 0;
     unsigned long long* counters = nullptr;  // [0] work counter, [1] overflow flag
     Stats* dstats = nullptr;
     rt_stats stats{};
@@ -546,7 +574,9 @@ struct rt_ctx {
     // (host-built scenes only; a device-built scene keeps the binary tree).  rt_set_bvh_width / RT_B200_BVH_WIDTH
     int bvh_width = RT_B200_DEFAULT_BVH_WIDTH;
     int wide_depth = 0;  // levels of the uploaded wide tree = stack entries a ray can need
-    bool pending_async = false;
+    bool pending_async = false;           // an RT_FLAG_ASYNC render has not been waited for yet (dev_wait)
+    bool pending_stats = false;
+    cudaStream_t pending_stream = nullptr;  // the stream it was enqueued on
     // scene-upload path: 0 auto (device from kDeviceBuildAuto primitives up), 1 host SAH, 2 device (LBVH + SAH top levels), 3 device, pure LBVH
     int bvh_builder = 0;
     size_t world_type_count[4] = {0, 0, 0, 0};  // primitives of each device type in the world list (validate_scene)
@@ -564,7 +594,7 @@ constexpr int kDeviceBuildAuto = 1 << 16;
 constexpr int kWideMaxDepth = 24;
 constexpr int kDeviceBuildMin = 8;
 
-static int fail(rt_ctx* ctx, int code, const char* fmt, ...) {
+static int fail(DevCtx* ctx, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -580,9 +610,9 @@ static int fail(rt_ctx* ctx, int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));      \
     } while (0)
 
-static void free_scene(rt_ctx* ctx) { ctx->has_scene = false; }
+static void free_scene(DevCtx* ctx) { ctx->has_scene = false; }
 
-static void release_buffers(rt_ctx* ctx) {
+static void release_buffers(DevCtx* ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->scratch) cudaFree(ctx->scratch);
     ctx->copy_ring.release();
@@ -596,6 +626,9 @@ static void release_buffers(rt_ctx* ctx) {
     if (ctx->staging) cudaFreeHost(ctx->staging);
     if (ctx->out_lin) cudaFree(ctx->out_lin);
     if (ctx->out_rgb8) cudaFree(ctx->out_rgb8);
+    if (ctx->frame_scratch) cudaFree(ctx->frame_scratch);
+    ctx->frame_scratch = nullptr;
+    ctx->frame_scratch_cap = 0;
     ctx->arena = ctx->staging = ctx->out_rgb8 = nullptr;
     ctx->out_lin = nullptr;
     ctx->arena_cap = ctx->staging_cap = ctx->out_pixels = 0;
@@ -611,10 +644,10 @@ struct ArenaPlan {
     }
 };
 
-extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
+static int dev_create(DevCtx** out, const int* device_ids, int n_devices) {
     if (!out) return RT_ERR_INVALID;
     *out = nullptr;
-    rt_ctx* ctx = new (std::nothrow) rt_ctx();
+    DevCtx* ctx = new (std::nothrow) DevCtx();
     if (!ctx) return RT_ERR_NOMEM;
     *out = ctx;  // returned even on failure so that rt_last_error works; caller destroys it
     if (n_devices != 1 || !device_ids) return fail(ctx, RT_ERR_INVALID, "rt_create: exactly one device per context (got %d)", n_devices);
@@ -690,7 +723,7 @@ extern "C" int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
     return RT_OK;
 }
 
-extern "C" void rt_destroy(rt_ctx* ctx) {
+static void dev_destroy(DevCtx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -705,7 +738,6 @@ extern "C" void rt_destroy(rt_ctx* ctx) {
     delete ctx;
 }
 
-extern "C" const char* rt_last_error(const rt_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
 
 // ---------------------------------------------------------------------------------
 // scene upload
@@ -736,7 +768,7 @@ bool texture_needs_uv(const rt_scene_desc* sc, int tex, int depth = 0) {
 
 }  // namespace
 
-static int validate_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
+static int validate_scene(DevCtx* ctx, const rt_scene_desc* sc) {
     if (!sc) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: null scene");
     if (sc->struct_size != sizeof(rt_scene_desc) || sc->abi_version != RT_B200_ABI_VERSION)
         return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: ABI mismatch (struct_size %u vs %zu, abi %u vs %d)", sc->struct_size,
@@ -823,7 +855,7 @@ static int validate_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
 }
 
 // Camera.txt:136-175 in double; stores the FP32 camera block for a width x height frame.
-static void setup_camera(rt_ctx* ctx, int width, int height) {
+static void setup_camera(DevCtx* ctx, int width, int height) {
     const rt_camera& c = ctx->camera;
     const double pi = 3.1415926535897932385;
     D3 lookfrom = d3(c.lookfrom), lookat = d3(c.lookat), vup = d3(c.vup);
@@ -863,7 +895,7 @@ static void setup_camera(rt_ctx* ctx, int width, int height) {
 
 // `too_deep` is set when the device-built tree is deeper than the traversal stack allows; the
 // caller then repeats the upload on the host path.
-static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_build, bool* too_deep) {
+static int upload_scene_impl(DevCtx* ctx, const rt_scene_desc* sc, bool device_build, bool* too_deep) {
     auto t_begin = std::chrono::steady_clock::now();
     const rtprep::Sources src{sc->spheres, sc->quads, sc->triangles, sc->xforms};
     size_t world_count[4] = {0, 0, 0, 0};  // device path: primitives of each device type the kernels will write
@@ -1218,13 +1250,17 @@ static int upload_scene_impl(rt_ctx* ctx, const rt_scene_desc* sc, bool device_b
     return RT_OK;
 }
 
-extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
+static int dev_wait(DevCtx* ctx);
+
+static int dev_upload_scene(DevCtx* ctx, const rt_scene_desc* sc) {
     if (!ctx) return RT_ERR_INVALID;
     auto t_begin = std::chrono::steady_clock::now();
     int rc = validate_scene(ctx, sc);
     if (rc != RT_OK) return rc;
     CU(ctx, cudaSetDevice(ctx->device));
-    if (ctx->pending_async) { CU(ctx, cudaStreamSynchronize(ctx->stream)); ctx->pending_async = false; }
+    // an asynchronous render may still be reading the arena -- on the caller's stream, not necessarily ours
+    rc = dev_wait(ctx);
+    if (rc != RT_OK) return rc;
     free_scene(ctx);
     // which path: host (bake + binned SAH on the CPU) or device (csrc/bvh_device.cuh)
     const bool device_build = sc->n_world >= kDeviceBuildMin && (ctx->bvh_builder >= 2 || (ctx->bvh_builder == 0 && sc->n_world >= kDeviceBuildAuto));
@@ -1237,7 +1273,7 @@ extern "C" int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* sc) {
 }
 
 // 0 auto, 1 host SAH, 2 device LBVH: which builder the next rt_upload_scene uses
-extern "C" int rt_set_bvh_builder(rt_ctx* ctx, int32_t mode) {
+static int dev_set_bvh_builder(DevCtx* ctx, int32_t mode) {
     if (!ctx) return RT_ERR_INVALID;
     if (mode < 0 || mode > 3) return fail(ctx, RT_ERR_INVALID, "rt_set_bvh_builder: mode %d (0 auto, 1 host, 2 device, 3 device without the SAH top)", mode);
     ctx->bvh_builder = mode;
@@ -1245,7 +1281,7 @@ extern "C" int rt_set_bvh_builder(rt_ctx* ctx, int32_t mode) {
 }
 
 // 2, 4 or 8: which acceleration structure the next rt_upload_scene builds for the render kernels
-extern "C" int rt_set_bvh_width(rt_ctx* ctx, int32_t width) {
+static int dev_set_bvh_width(DevCtx* ctx, int32_t width) {
     if (!ctx) return RT_ERR_INVALID;
     if (width != 2 && width != 4 && width != 8) return fail(ctx, RT_ERR_INVALID, "rt_set_bvh_width: %d (2 binary, 4 or 8 wide quantised)", width);
     ctx->bvh_width = width;
@@ -1255,46 +1291,56 @@ extern "C" int rt_set_bvh_width(rt_ctx* ctx, int32_t width) {
 // ---------------------------------------------------------------------------------
 // rendering
 // ---------------------------------------------------------------------------------
-static int ensure_accum(rt_ctx* ctx, int width, int height) {
-    size_t need = (size_t)width * height * 4 * sizeof(unsigned long long);
+extern "C" size_t rt_shard_pixels(int32_t width, int32_t height, int32_t tile_size, int32_t shard_rank, int32_t shard_count) {
+    if (width <= 0 || height <= 0 || tile_size <= 0 || shard_count <= 0 || shard_rank < 0 || shard_rank >= shard_count) return 0;
+    AccumLayout L;
+    L.width = width; L.height = height; L.compact = true; L.rank = shard_rank; L.count = shard_count; L.tile = tile_size;
+    return L.slots();
+}
+
+static int ensure_accum(DevCtx* ctx, const AccumLayout& L) {
+    const size_t need = std::max<size_t>(L.slots(), 1) * 4 * sizeof(unsigned long long);
     if (ctx->accum_external) {
-        if (ctx->acc_w != width || ctx->acc_h != height)
-            return fail(ctx, RT_ERR_STATE, "rt_render: bound accumulation buffer is %dx%d, frame is %dx%d", ctx->acc_w, ctx->acc_h, width, height);
+        if (L.compact || ctx->acc.width != L.width || ctx->acc.height != L.height)
+            return fail(ctx, RT_ERR_STATE, "rt_render: the bound accumulation buffer is a full %dx%d frame, this render needs %s%dx%d", ctx->acc.width,
+                        ctx->acc.height, L.compact ? "compact tiles of " : "", L.width, L.height);
         return RT_OK;
     }
-    if (ctx->accum && ctx->acc_w == width && ctx->acc_h == height) return RT_OK;
-    if (ctx->accum) cudaFree(ctx->accum);
-    ctx->accum = nullptr;
-    cudaError_t e = cudaMalloc(&ctx->accum, need);
-    if (e != cudaSuccess) return fail(ctx, RT_ERR_NOMEM, "rt_render: cannot allocate %zu bytes for the accumulation buffer", need);
+    if (ctx->accum && ctx->acc == L) return RT_OK;
+    if (!ctx->accum || need > ctx->accum_cap) {
+        if (ctx->accum) cudaFree(ctx->accum);
+        ctx->accum = nullptr;
+        ctx->accum_cap = 0;
+        if (cudaMalloc(&ctx->accum, need) != cudaSuccess) return fail(ctx, RT_ERR_NOMEM, "rt_render: cannot allocate %zu bytes for the accumulation buffer", need);
+        ctx->accum_cap = need;
+    }
     ctx->accum_bytes = need;
-    ctx->acc_w = width;
-    ctx->acc_h = height;
+    ctx->acc = L;
     cudaMemsetAsync(ctx->accum, 0, need, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     return RT_OK;
 }
 
-extern "C" int rt_bind_accum(rt_ctx* ctx, void* device_ptr, size_t bytes, int32_t width, int32_t height) {
+static int dev_bind_accum(DevCtx* ctx, void* device_ptr, size_t bytes, int32_t width, int32_t height) {
     if (!ctx) return RT_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
     if (ctx->accum && !ctx->accum_external) cudaFree(ctx->accum);
     ctx->accum = nullptr;
     ctx->accum_external = false;
-    ctx->acc_w = ctx->acc_h = 0;
-    ctx->accum_bytes = 0;
+    ctx->acc = AccumLayout();
+    ctx->accum_bytes = ctx->accum_cap = 0;
     if (!device_ptr) return RT_OK;
     size_t need = (size_t)width * height * 4 * sizeof(unsigned long long);
     if (width <= 0 || height <= 0 || bytes < need) return fail(ctx, RT_ERR_INVALID, "rt_bind_accum: need %zu bytes for %dx%d, got %zu", need, width, height, bytes);
     ctx->accum = (unsigned long long*)device_ptr;
     ctx->accum_external = true;
     ctx->accum_bytes = need;
-    ctx->acc_w = width;
-    ctx->acc_h = height;
+    ctx->acc.width = width;
+    ctx->acc.height = height;
     return RT_OK;
 }
 
-extern "C" int rt_accum_buffer(rt_ctx* ctx, void** device_ptr, size_t* bytes) {
+static int dev_accum_buffer(DevCtx* ctx, void** device_ptr, size_t* bytes) {
     if (!ctx || !device_ptr || !bytes) return RT_ERR_INVALID;
     if (!ctx->accum) return fail(ctx, RT_ERR_STATE, "rt_accum_buffer: nothing rendered or bound yet");
     *device_ptr = ctx->accum;
@@ -1302,29 +1348,116 @@ extern "C" int rt_accum_buffer(rt_ctx* ctx, void** device_ptr, size_t* bytes) {
     return RT_OK;
 }
 
-// Checkpoint / resume of a progressive render (SURVEY 8f rank 3): the frame so far IS the
-// accumulation buffer (integer sums), so a raw copy of it plus the index of the next sample is a
-// complete checkpoint, and a resumed render is bit-identical to an uninterrupted one.
-extern "C" int rt_accum_download(rt_ctx* ctx, uint64_t* host, size_t bytes) {
-    if (!ctx || !host) return RT_ERR_INVALID;
-    if (!ctx->accum) return fail(ctx, RT_ERR_STATE, "rt_accum_download: nothing rendered or bound yet");
-    if (bytes < ctx->accum_bytes) return fail(ctx, RT_ERR_INVALID, "rt_accum_download: need %zu bytes, got %zu", ctx->accum_bytes, bytes);
-    CU(ctx, cudaSetDevice(ctx->device));
-    CU(ctx, cudaDeviceSynchronize());
-    ctx->pending_async = false;
-    CU(ctx, cudaMemcpy(host, ctx->accum, ctx->accum_bytes, cudaMemcpyDeviceToHost));
+// Scatter the compact tile buffers of `count` shards (shard r starts at shards + r * stride bytes) into a full
+// row-major frame of `bpp`-byte pixels: pixel (x, y) lies in tile t = (y / tile) * tiles_x + x / tile, which is local
+// tile t / count of shard t mod count.  only_rank >= 0: take that shard's tiles from `shards` directly (stride
+// unused) and leave the other pixels as they are.  bpp: 3 (RGB8), 12 (float RGB) or 32 (the uint64 sums).
+template <int BPP>
+__global__ void untile_kernel(const unsigned char* __restrict__ shards, size_t stride, int count, int only_rank, int width, int height,
+                              int tile, unsigned char* __restrict__ dst) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    const int tiles_x = (width + tile - 1) / tile;
+    const int t = (y / tile) * tiles_x + x / tile;
+    const int r = t % count;
+    if (only_rank >= 0 && r != only_rank) return;
+    const size_t slot = ((size_t)(t / count) * tile + (size_t)(y % tile)) * tile + (size_t)(x % tile);
+    const unsigned char* src = shards + (only_rank >= 0 ? 0 : (size_t)r * stride) + slot * BPP;
+    unsigned char* out = dst + ((size_t)y * width + x) * BPP;
+    if (BPP == 32) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(out);
+        d4[0] = s4[0];
+        d4[1] = s4[1];
+    } else if (BPP == 12) {
+        const float* sf = reinterpret_cast<const float*>(src);
+        float* df = reinterpret_cast<float*>(out);
+        df[0] = sf[0]; df[1] = sf[1]; df[2] = sf[2];
+    } else {
+        out[0] = src[0]; out[1] = src[1]; out[2] = src[2];
+    }
+}
+// the inverse for the sums: gather one shard's tiles out of a full frame (restoring a checkpoint into a compact buffer)
+__global__ void tile_pack_kernel(const unsigned long long* __restrict__ full, int rank, int count, int width, int height, int tile,
+                                 unsigned long long* __restrict__ compact) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    const int tiles_x = (width + tile - 1) / tile;
+    const int t = (y / tile) * tiles_x + x / tile;
+    if (t % count != rank) return;
+    const size_t slot = ((size_t)(t / count) * tile + (size_t)(y % tile)) * tile + (size_t)(x % tile);
+    const uint4* s4 = reinterpret_cast<const uint4*>(full + 4 * ((size_t)y * width + x));
+    uint4* d4 = reinterpret_cast<uint4*>(compact + 4 * slot);
+    d4[0] = s4[0];
+    d4[1] = s4[1];
+}
+// a += b over n uint64 (fixed-point sums are associative: the order of the shards does not matter)
+__global__ void add_sums_kernel(unsigned long long* __restrict__ a, const unsigned long long* __restrict__ b, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += b[i];
+}
+
+static cudaError_t launch_untile(int bpp, const void* shards, size_t stride, int count, int only_rank, int width, int height, int tile, void* dst,
+                                 cudaStream_t stream) {
+    dim3 block(32, 8), grid((width + 31) / 32, (height + 7) / 8);
+    const unsigned char* s = (const unsigned char*)shards;
+    unsigned char* d = (unsigned char*)dst;
+    if (bpp == 32) untile_kernel<32><<<grid, block, 0, stream>>>(s, stride, count, only_rank, width, height, tile, d);
+    else if (bpp == 12) untile_kernel<12><<<grid, block, 0, stream>>>(s, stride, count, only_rank, width, height, tile, d);
+    else untile_kernel<3><<<grid, block, 0, stream>>>(s, stride, count, only_rank, width, height, tile, d);
+    return cudaGetLastError();
+}
+
+// device scratch that grows on demand (full-frame copies of compact data, gather staging)
+static int ensure_scratch_out(DevCtx* ctx, size_t bytes) {
+    if (bytes <= ctx->frame_scratch_cap) return RT_OK;
+    if (ctx->frame_scratch) cudaFree(ctx->frame_scratch);
+    ctx->frame_scratch = nullptr;
+    ctx->frame_scratch_cap = 0;
+    if (cudaMalloc(&ctx->frame_scratch, bytes) != cudaSuccess) return fail(ctx, RT_ERR_NOMEM, "cannot allocate %zu bytes of frame scratch", bytes);
+    ctx->frame_scratch_cap = bytes;
     return RT_OK;
 }
 
-extern "C" int rt_accum_upload(rt_ctx* ctx, const uint64_t* host, size_t bytes, int32_t width, int32_t height) {
+static int dev_wait(DevCtx* ctx);
+
+// Checkpoint / resume of a progressive render (SURVEY 8f rank 3): the frame so far IS the
+// accumulation buffer (integer sums), so a raw copy of it plus the index of the next sample is a
+// complete checkpoint, and a resumed render is bit-identical to an uninterrupted one.  Always the
+// FULL row-major frame on the host side: a compact buffer is scattered into a zeroed frame first.
+static int dev_accum_download(DevCtx* ctx, uint64_t* host, size_t bytes) {
+    if (!ctx || !host) return RT_ERR_INVALID;
+    if (!ctx->accum) return fail(ctx, RT_ERR_STATE, "rt_accum_download: nothing rendered or bound yet");
+    const size_t full = (size_t)ctx->acc.width * ctx->acc.height * 32;
+    if (bytes < full) return fail(ctx, RT_ERR_INVALID, "rt_accum_download: need %zu bytes, got %zu", full, bytes);
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = dev_wait(ctx);
+    if (rc != RT_OK) return rc;
+    const unsigned long long* src = ctx->accum;
+    if (ctx->acc.compact) {
+        rc = ensure_scratch_out(ctx, full);
+        if (rc != RT_OK) return rc;
+        CU(ctx, cudaMemsetAsync(ctx->frame_scratch, 0, full, ctx->stream));
+        CU(ctx, launch_untile(32, ctx->accum, 0, ctx->acc.count, ctx->acc.rank, ctx->acc.width, ctx->acc.height, ctx->acc.tile, ctx->frame_scratch, ctx->stream));
+        src = (const unsigned long long*)ctx->frame_scratch;
+    }
+    CU(ctx, cudaMemcpyAsync(host, src, full, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+static int dev_accum_upload(DevCtx* ctx, const uint64_t* host, size_t bytes, int32_t width, int32_t height) {
     if (!ctx || !host) return RT_ERR_INVALID;
     if (width <= 0 || height <= 0 || (long long)width * height >= (1ll << 31)) return fail(ctx, RT_ERR_INVALID, "rt_accum_upload: bad frame size %dx%d", width, height);
     const size_t need = (size_t)width * height * 4 * sizeof(unsigned long long);
     if (bytes != need) return fail(ctx, RT_ERR_INVALID, "rt_accum_upload: a %dx%d frame is %zu bytes, got %zu", width, height, need, bytes);
     CU(ctx, cudaSetDevice(ctx->device));
-    CU(ctx, cudaDeviceSynchronize());
-    ctx->pending_async = false;
-    int rc = ensure_accum(ctx, width, height);
+    int rc = dev_wait(ctx);
+    if (rc != RT_OK) return rc;
+    AccumLayout L;
+    L.width = width;
+    L.height = height;
+    rc = ensure_accum(ctx, L);
     if (rc != RT_OK) return rc;
     // on the context's stream (cudaMemcpy from pageable memory returns once the data is STAGED; the DMA itself is
     // ordered only against the legacy stream, and ctx->stream is non-blocking: a render enqueued right after could
@@ -1334,14 +1467,57 @@ extern "C" int rt_accum_upload(rt_ctx* ctx, const uint64_t* host, size_t bytes, 
     return RT_OK;
 }
 
-extern "C" int rt_sync(rt_ctx* ctx) {
-    if (!ctx) return RT_ERR_INVALID;
+// Finish what an RT_FLAG_ASYNC render left pending: wait for the stream it ran on, read the device time, the
+// guard counters and (STATS) the counters.  Everything that touches the frame or the scene calls this first.
+static int dev_wait(DevCtx* ctx) {
     CU(ctx, cudaSetDevice(ctx->device));
-    CU(ctx, cudaDeviceSynchronize());
+    if (!ctx->pending_async) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return RT_OK;
+    }
     ctx->pending_async = false;
+    CU(ctx, cudaEventSynchronize(ctx->ev1));
+    if (ctx->pending_stream != ctx->stream) CU(ctx, cudaStreamSynchronize(ctx->pending_stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CU(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.render_ms = ms;
     unsigned long long c[2] = {0, 0};
-    CU(ctx, cudaMemcpy(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost));
+    CU(ctx, cudaMemcpyAsync(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (c[1]) return fail(ctx, RT_ERR_KERNEL, "traversal stack overflow (BVH deeper than %d)", STACK_SIZE);
+    if (ctx->pending_stats) {
+        Stats h;
+        CU(ctx, cudaMemcpyAsync(&h, ctx->dstats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ctx->stats.trav_hist, ctx->dstats + 1, sizeof ctx->stats.trav_hist, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->stats.rays = h.rays;
+        ctx->stats.node_visits = h.node_visits;
+        ctx->stats.box_tests = h.box_tests;
+        ctx->stats.sphere_tests = h.sphere_tests;
+        ctx->stats.quad_tests = h.quad_tests;
+        ctx->stats.triangle_tests = h.tri_tests;
+        ctx->stats.medium_queries = h.medium_queries;
+        ctx->stats.boundary_tests = h.boundary_tests;
+        ctx->stats.fp64_sphere_tests = h.fp64_sphere;
+        ctx->stats.empty_node_steps = h.empty_steps;
+        ctx->stats.nonfinite_samples = h.nonfinite;
+        ctx->stats.desc_iters = h.desc_iters;
+        ctx->stats.desc_lanes = h.desc_lanes;
+        ctx->stats.desc_trav_lanes = h.desc_trav_lanes;
+        ctx->stats.leaf_iters = h.leaf_iters;
+        ctx->stats.leaf_lanes = h.leaf_lanes;
+        ctx->stats.shade_iters = h.shade_iters;
+        ctx->stats.shade_lanes = h.shade_lanes;
+    }
+    return RT_OK;
+}
+
+static int dev_sync(DevCtx* ctx) {
+    if (!ctx) return RT_ERR_INVALID;
+    int rc = dev_wait(ctx);
+    if (rc != RT_OK) return rc;
+    CU(ctx, cudaDeviceSynchronize());
     return RT_OK;
 }
 
@@ -1350,7 +1526,7 @@ extern "C" int rt_sync(rt_ctx* ctx) {
 // of the pool until the sample stream is exhausted and no path is alive
 // ---------------------------------------------------------------------------------
 #ifdef RT_B200_ALT_KERNELS
-static int launch_wavefront(rt_ctx* ctx, const RenderArgs& A, cudaStream_t stream, bool stats, unsigned long long pixel_blocks) {
+static int launch_wavefront(DevCtx* ctx, const RenderArgs& A, cudaStream_t stream, bool stats, unsigned long long pixel_blocks) {
     rtwf::Stream W;
     std::memset(&W, 0, sizeof W);
     W.width = A.width; W.height = A.height; W.max_depth = A.max_depth; W.spp_begin = A.spp_begin;
@@ -1431,10 +1607,10 @@ static RenderKernel v2_kernel(int variant, int width) {
     return width == 8 ? v2_instance<8>(variant) : (width == 4 ? v2_instance<4>(variant) : v2_instance<2>(variant));
 }
 // dynamic shared memory of a wide instance: the traversal stacks, [entry][thread]
-static size_t v2_smem(const rt_ctx* ctx, int width) { return width <= 2 ? (size_t)RT_SMEM_STACK * RT_V2_THREADS * 8 : (size_t)std::max(ctx->wide_depth, 1) * RT_V2_THREADS * sizeof(uint2); }
+static size_t v2_smem(const DevCtx* ctx, int width) { return width <= 2 ? (size_t)RT_SMEM_STACK * RT_V2_THREADS * 8 : (size_t)std::max(ctx->wide_depth, 1) * RT_V2_THREADS * sizeof(uint2); }
 
 // blocks per SM the kernel instance runs with (the grid is persistent: SMs x this)
-static int v2_blocks_per_sm(rt_ctx* ctx, int variant, int width, int* out) {
+static int v2_blocks_per_sm(DevCtx* ctx, int variant, int width, int* out) {
     width = v2_effective_width(variant, width);
     RenderKernel k = v2_kernel(variant, width);
     const size_t smem = v2_smem(ctx, width);
@@ -1447,7 +1623,7 @@ static int v2_blocks_per_sm(rt_ctx* ctx, int variant, int width, int* out) {
     return RT_OK;
 }
 
-static int launch_v2(rt_ctx* ctx, int variant, int width, int grid, const RenderArgs& A, cudaStream_t stream) {
+static int launch_v2(DevCtx* ctx, int variant, int width, int grid, const RenderArgs& A, cudaStream_t stream) {
     width = v2_effective_width(variant, width);
     size_t smem = v2_smem(ctx, width);
     // RT_B200_DUMMY_SMEM: unused dynamic shared memory per block, to measure what giving up
@@ -1462,7 +1638,7 @@ static int launch_v2(rt_ctx* ctx, int variant, int width, int grid, const Render
     return RT_OK;
 }
 
-extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
+static int dev_render(DevCtx* ctx, const rt_render_params* p) {
     if (!ctx) return RT_ERR_INVALID;
     if (!p || p->struct_size != sizeof(rt_render_params)) return fail(ctx, RT_ERR_INVALID, "rt_render: bad params struct");
     if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "rt_render: no scene uploaded");
@@ -1474,7 +1650,9 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
     if (rank < 0 || rank >= count) return fail(ctx, RT_ERR_INVALID, "rt_render: shard_rank %d outside [0,%d)", rank, count);
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t stream = p->stream ? (cudaStream_t)p->stream : ctx->stream;
-    int rc = ensure_accum(ctx, p->width, p->height);
+    // a pending asynchronous render (possibly on another stream) shares the work counter, the guard flags and the
+    // stats block with this one: finish it first
+    int rc = dev_wait(ctx);
     if (rc != RT_OK) return rc;
     if (ctx->cam_w != p->width || ctx->cam_h != p->height) setup_camera(ctx, p->width, p->height);
 
@@ -1511,6 +1689,22 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
     } else {
         return fail(ctx, RT_ERR_INVALID, "rt_render: unknown shard_mode %d", p->shard_mode);
     }
+    AccumLayout L;
+    L.width = p->width;
+    L.height = p->height;
+    if (p->flags & RT_FLAG_COMPACT_TILES) {
+        if (mode != RT_SHARD_TILES) return fail(ctx, RT_ERR_INVALID, "rt_render: RT_FLAG_COMPACT_TILES needs tile sharding (shard_mode RT_SHARD_TILES)");
+        if (ctx->kernel_version != 2) return fail(ctx, RT_ERR_UNSUPPORTED, "rt_render: compact tile buffers are implemented by render_kernel_v2 only");
+        L.compact = true;
+        L.rank = rank;
+        L.count = count;
+        L.tile = A.tile_size;
+        A.compact = 1;
+    }
+    if ((p->flags & RT_FLAG_ACCUMULATE) && ctx->accum && !(ctx->acc == L))
+        return fail(ctx, RT_ERR_STATE, "rt_render: RT_FLAG_ACCUMULATE onto a buffer of another frame size or tile layout");
+    rc = ensure_accum(ctx, L);
+    if (rc != RT_OK) return rc;
     const bool stats = (p->flags & RT_FLAG_STATS) != 0;
     int bps = ctx->blocks_per_sm[stats ? 1 : 0];
     // which instance of render_kernel_v2 runs: LITE = no triangles, no point lights, no defocus blur in this scene (see hit_prim)
@@ -1542,11 +1736,11 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
     A.k0 = (uint32_t)(p->seed & 0xffffffffu);
     A.k1 = (uint32_t)(p->seed >> 32);
 
-    if (!(p->flags & RT_FLAG_ACCUMULATE)) CU(ctx, cudaMemsetAsync(ctx->accum, 0, (size_t)p->width * p->height * 32, stream));
+    if (!(p->flags & RT_FLAG_ACCUMULATE)) CU(ctx, cudaMemsetAsync(ctx->accum, 0, L.slots() * 32, stream));
     CU(ctx, cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), stream));
     if (stats) CU(ctx, cudaMemsetAsync(ctx->dstats, 0, sizeof(Stats) + kTravHistBins * sizeof(unsigned long long), stream));
     const bool async = (p->flags & RT_FLAG_ASYNC) != 0;
-    if (!async) CU(ctx, cudaEventRecord(ctx->ev0, stream));
+    CU(ctx, cudaEventRecord(ctx->ev0, stream));
     ctx->stats.kernel_launches = 0;
     if (A.n_items > 0) {
 #ifdef RT_B200_ALT_KERNELS
@@ -1584,75 +1778,105 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
         }
         ctx->stats.samples = px * (uint64_t)A.n_local_samples;
     }
-    if (async) {
-        ctx->pending_async = true;
-        return RT_OK;
-    }
     CU(ctx, cudaEventRecord(ctx->ev1, stream));
-    CU(ctx, cudaEventSynchronize(ctx->ev1));
-    float ms = 0;
-    CU(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ctx->stats.render_ms = ms;
-    unsigned long long c[2] = {0, 0};
-    CU(ctx, cudaMemcpy(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost));
-    if (c[1]) return fail(ctx, RT_ERR_KERNEL, "traversal stack overflow (BVH deeper than %d)", STACK_SIZE);
-    if (stats) {
-        Stats h;
-        CU(ctx, cudaMemcpy(&h, ctx->dstats, sizeof h, cudaMemcpyDeviceToHost));
-        ctx->stats.rays = h.rays;
-        ctx->stats.node_visits = h.node_visits;
-        ctx->stats.box_tests = h.box_tests;
-        ctx->stats.sphere_tests = h.sphere_tests;
-        ctx->stats.quad_tests = h.quad_tests;
-        ctx->stats.triangle_tests = h.tri_tests;
-        ctx->stats.medium_queries = h.medium_queries;
-        ctx->stats.boundary_tests = h.boundary_tests;
-        ctx->stats.fp64_sphere_tests = h.fp64_sphere;
-        ctx->stats.empty_node_steps = h.empty_steps;
-        ctx->stats.nonfinite_samples = h.nonfinite;
-        ctx->stats.desc_iters = h.desc_iters;
-        ctx->stats.desc_lanes = h.desc_lanes;
-        ctx->stats.desc_trav_lanes = h.desc_trav_lanes;
-        ctx->stats.leaf_iters = h.leaf_iters;
-        ctx->stats.leaf_lanes = h.leaf_lanes;
-        ctx->stats.shade_iters = h.shade_iters;
-        ctx->stats.shade_lanes = h.shade_lanes;
-        CU(ctx, cudaMemcpy(ctx->stats.trav_hist, ctx->dstats + 1, sizeof ctx->stats.trav_hist, cudaMemcpyDeviceToHost));
-    }
+    ctx->pending_async = true;
+    ctx->pending_stats = stats;
+    ctx->pending_stream = stream;
+    if (async) return RT_OK;
+    return dev_wait(ctx);
+}
+
+// resolve_kernel over the slots of the accumulation buffer (full frame or compact tiles) into DEVICE buffers
+static int dev_resolve_into(DevCtx* ctx, int32_t total_spp, float* dev_lin, unsigned char* dev_rgb8) {
+    const size_t n = ctx->acc.slots();
+    if (n == 0 || (!dev_lin && !dev_rgb8)) return RT_OK;
+    const double inv = 1.0 / ((double)kAccumScale * (double)total_spp);
+    resolve_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->accum, (int)n, inv, dev_lin, dev_rgb8);
+    CU(ctx, cudaGetLastError());
     return RT_OK;
 }
 
-extern "C" int rt_download(rt_ctx* ctx, int32_t total_spp, float* rgb_linear, uint8_t* rgb8) {
+static int ensure_out(DevCtx* ctx, size_t pixels) {
+    if (pixels <= ctx->out_pixels) return RT_OK;
+    if (ctx->out_lin) cudaFree(ctx->out_lin);
+    if (ctx->out_rgb8) cudaFree(ctx->out_rgb8);
+    ctx->out_lin = nullptr;
+    ctx->out_rgb8 = nullptr;
+    ctx->out_pixels = 0;
+    if (cudaMalloc(&ctx->out_lin, pixels * 3 * sizeof(float)) != cudaSuccess || cudaMalloc(&ctx->out_rgb8, pixels * 3) != cudaSuccess)
+        return fail(ctx, RT_ERR_NOMEM, "rt_download: cannot allocate the output buffers");
+    ctx->out_pixels = pixels;
+    return RT_OK;
+}
+
+// The compact tiles of this shard resolved into caller-owned DEVICE buffers (for a gather over NCCL by the caller:
+// one process per GPU).  capacity_pixels >= rt_shard_pixels(...) of the rendered layout.
+static int dev_resolve_tiles(DevCtx* ctx, int32_t total_spp, float* dev_rgb_linear, uint8_t* dev_rgb8, size_t capacity_pixels) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (!ctx->accum) return fail(ctx, RT_ERR_STATE, "rt_resolve_tiles: nothing rendered yet");
+    if (total_spp <= 0) return fail(ctx, RT_ERR_INVALID, "rt_resolve_tiles: total_spp must be positive");
+    if (capacity_pixels < ctx->acc.slots()) return fail(ctx, RT_ERR_INVALID, "rt_resolve_tiles: the buffers hold %zu pixels, the frame has %zu", capacity_pixels, ctx->acc.slots());
+    int rc = dev_wait(ctx);
+    if (rc != RT_OK) return rc;
+    rc = dev_resolve_into(ctx, total_spp, dev_rgb_linear, dev_rgb8);
+    if (rc != RT_OK) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+// Compact buffers of `shard_count` shards, gathered on this context's device (shard r at dev_shards + r * stride),
+// scattered into the full row-major frame and copied to the host.  bytes_per_pixel 3, 12 or 32.
+static int dev_untile(DevCtx* ctx, const void* dev_shards, size_t shard_stride_bytes, int32_t bytes_per_pixel, int32_t shard_count, int32_t width,
+                      int32_t height, int32_t tile_size, void* host_out) {
+    if (!ctx || !dev_shards || !host_out) return RT_ERR_INVALID;
+    if (width <= 0 || height <= 0 || tile_size <= 0 || shard_count <= 0 || (bytes_per_pixel != 3 && bytes_per_pixel != 12 && bytes_per_pixel != 32))
+        return fail(ctx, RT_ERR_INVALID, "rt_untile: bad arguments");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t full = (size_t)width * height * bytes_per_pixel;
+    int rc = ensure_scratch_out(ctx, full);
+    if (rc != RT_OK) return rc;
+    CU(ctx, launch_untile(bytes_per_pixel, dev_shards, shard_stride_bytes, shard_count, -1, width, height, tile_size, ctx->frame_scratch, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(host_out, ctx->frame_scratch, full, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+static int dev_download(DevCtx* ctx, int32_t total_spp, float* rgb_linear, uint8_t* rgb8) {
     if (!ctx) return RT_ERR_INVALID;
     if (!ctx->accum) return fail(ctx, RT_ERR_STATE, "rt_download: nothing rendered yet");
     if (total_spp <= 0) return fail(ctx, RT_ERR_INVALID, "rt_download: total_spp must be positive");
-    CU(ctx, cudaSetDevice(ctx->device));
-    CU(ctx, cudaDeviceSynchronize());
-    ctx->pending_async = false;
-    const int n = ctx->acc_w * ctx->acc_h;
-    if ((size_t)n > ctx->out_pixels) {
-        if (ctx->out_lin) cudaFree(ctx->out_lin);
-        if (ctx->out_rgb8) cudaFree(ctx->out_rgb8);
-        ctx->out_lin = nullptr;
-        ctx->out_rgb8 = nullptr;
-        ctx->out_pixels = 0;
-        if (cudaMalloc(&ctx->out_lin, (size_t)n * 3 * sizeof(float)) != cudaSuccess || cudaMalloc(&ctx->out_rgb8, (size_t)n * 3) != cudaSuccess)
-            return fail(ctx, RT_ERR_NOMEM, "rt_download: cannot allocate the output buffers");
-        ctx->out_pixels = (size_t)n;
-    }
+    int rc = dev_wait(ctx);
+    if (rc != RT_OK) return rc;
+    const size_t n = ctx->acc.slots(), full = (size_t)ctx->acc.width * ctx->acc.height;
+    rc = ensure_out(ctx, n);
+    if (rc != RT_OK) return rc;
     float* dlin = rgb_linear ? ctx->out_lin : nullptr;
     unsigned char* d8 = rgb8 ? ctx->out_rgb8 : nullptr;
-    double inv = 1.0 / ((double)kAccumScale * (double)total_spp);
-    resolve_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->accum, n, inv, dlin, d8);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess && rgb_linear) e = cudaMemcpyAsync(rgb_linear, dlin, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess && rgb8) e = cudaMemcpyAsync(rgb8, d8, (size_t)n * 3, cudaMemcpyDeviceToHost, ctx->stream);
+    rc = dev_resolve_into(ctx, total_spp, dlin, d8);
+    if (rc != RT_OK) return rc;
+    cudaError_t e = cudaSuccess;
+    if (ctx->acc.compact) {
+        // one shard of a frame: its tiles go to their places in a zeroed full frame (black elsewhere)
+        const AccumLayout& L = ctx->acc;
+        rc = ensure_scratch_out(ctx, full * 15 + 256);
+        if (rc != RT_OK) return rc;
+        unsigned char* f8 = ctx->frame_scratch;
+        unsigned char* flin = ctx->frame_scratch + ((full * 3 + 255) & ~(size_t)255);
+        e = cudaMemsetAsync(ctx->frame_scratch, 0, ctx->frame_scratch_cap, ctx->stream);
+        if (e == cudaSuccess && rgb8) e = launch_untile(3, d8, 0, L.count, L.rank, L.width, L.height, L.tile, f8, ctx->stream);
+        if (e == cudaSuccess && rgb_linear) e = launch_untile(12, dlin, 0, L.count, L.rank, L.width, L.height, L.tile, flin, ctx->stream);
+        if (e == cudaSuccess && rgb_linear) e = cudaMemcpyAsync(rgb_linear, flin, full * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && rgb8) e = cudaMemcpyAsync(rgb8, f8, full * 3, cudaMemcpyDeviceToHost, ctx->stream);
+    } else {
+        if (rgb_linear) e = cudaMemcpyAsync(rgb_linear, dlin, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && rgb8) e = cudaMemcpyAsync(rgb8, d8, n * 3, cudaMemcpyDeviceToHost, ctx->stream);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "rt_download: %s", cudaGetErrorString(e));
     return RT_OK;
 }
 
-extern "C" int rt_render_aov(rt_ctx* ctx, int32_t width, int32_t height, int32_t* prim_id, float* t, float* normal, float* point,
+static int dev_render_aov(DevCtx* ctx, int32_t width, int32_t height, int32_t* prim_id, float* t, float* normal, float* point,
                              float* uv) {
     if (!ctx) return RT_ERR_INVALID;
     if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "rt_render_aov: no scene uploaded");
@@ -1694,7 +1918,7 @@ extern "C" int rt_render_aov(rt_ctx* ctx, int32_t width, int32_t height, int32_t
     return RT_OK;
 }
 
-extern "C" int rt_get_stats(rt_ctx* ctx, rt_stats* out) {
+static int dev_get_stats(DevCtx* ctx, rt_stats* out) {
     if (!ctx || !out) return RT_ERR_INVALID;
     *out = ctx->stats;
     return RT_OK;
@@ -1707,7 +1931,7 @@ extern "C" size_t rt_struct_size(int which) {
     return (which >= 0 && which < (int)(sizeof(sizes) / sizeof(sizes[0]))) ? sizes[which] : 0;
 }
 
-extern "C" int rt_measure_fp32_peak(rt_ctx* ctx, double* tflops) {
+static int dev_measure_fp32_peak(DevCtx* ctx, double* tflops) {
     if (!ctx || !tflops) return RT_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
     float* d = nullptr;
@@ -1732,7 +1956,7 @@ extern "C" int rt_measure_fp32_peak(rt_ctx* ctx, double* tflops) {
 
 // ---- probes -----------------------------------------------------------------------
 template <class Launch>
-static int run_probe(rt_ctx* ctx, const char* name, const std::vector<std::pair<const void*, size_t>>& inputs,
+static int run_probe(DevCtx* ctx, const char* name, const std::vector<std::pair<const void*, size_t>>& inputs,
                      const std::vector<std::pair<void*, size_t>>& outputs, Launch launch) {
     CU(ctx, cudaSetDevice(ctx->device));
     std::vector<void*> din(inputs.size(), nullptr), dout(outputs.size(), nullptr);
@@ -1759,7 +1983,7 @@ static int run_probe(rt_ctx* ctx, const char* name, const std::vector<std::pair<
     return RT_OK;
 }
 
-extern "C" int rt_probe_texture(rt_ctx* ctx, int32_t texture, int32_t n, const float* uvp, float* rgb) {
+static int dev_probe_texture(DevCtx* ctx, int32_t texture, int32_t n, const float* uvp, float* rgb) {
     if (!ctx) return RT_ERR_INVALID;
     if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "rt_probe_texture: no scene uploaded");
     if (n <= 0 || !uvp || !rgb) return fail(ctx, RT_ERR_INVALID, "rt_probe_texture: bad arguments");
@@ -1769,7 +1993,7 @@ extern "C" int rt_probe_texture(rt_ctx* ctx, int32_t texture, int32_t n, const f
                      });
 }
 
-extern "C" int rt_probe_scatter(rt_ctx* ctx, int32_t material, int32_t n, const float* in_rec, const float* uniforms, float* out_rec) {
+static int dev_probe_scatter(DevCtx* ctx, int32_t material, int32_t n, const float* in_rec, const float* uniforms, float* out_rec) {
     if (!ctx) return RT_ERR_INVALID;
     if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "rt_probe_scatter: no scene uploaded");
     if (n <= 0 || !in_rec || !uniforms || !out_rec) return fail(ctx, RT_ERR_INVALID, "rt_probe_scatter: bad arguments");
@@ -1780,7 +2004,7 @@ extern "C" int rt_probe_scatter(rt_ctx* ctx, int32_t material, int32_t n, const 
                      });
 }
 
-extern "C" int rt_probe_hit(rt_ctx* ctx, int32_t n, const float* rays, int32_t* prim_id, float* t, float* normal, float* uv) {
+static int dev_probe_hit(DevCtx* ctx, int32_t n, const float* rays, int32_t* prim_id, float* t, float* normal, float* uv) {
     if (!ctx) return RT_ERR_INVALID;
     if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "rt_probe_hit: no scene uploaded");
     if (n <= 0 || !rays) return fail(ctx, RT_ERR_INVALID, "rt_probe_hit: bad arguments");
@@ -1792,3 +2016,5 @@ extern "C" int rt_probe_hit(rt_ctx* ctx, int32_t n, const float* rays, int32_t* 
                        });
     return rc;
 }
+
+#include "rt_api.cuh"
