@@ -33,6 +33,7 @@ int main(int argc, char** argv) {
     if (argc > 5) { cam.image_width = std::atoi(argv[4]); cam.aspect_ratio = double(cam.image_width) / std::atoi(argv[5]); }
     if (argc > 6) cam.samples_per_pixel = std::atoi(argv[6]);
     // additions: --checkpoint FILE [--every N] [--stop-after N] [--linear FILE.exr|.pfm] [--nee 0|1]
+    //            --devices all | 0,1,2,...   split the frame over several GPUs of this box (one context, tiles gathered over NVLink)
     for (int i = 7; i + 1 < argc; i += 2) {
         std::string k = argv[i];
         if (k == "--checkpoint") cam.checkpoint_path = argv[i + 1];
@@ -41,6 +42,22 @@ int main(int argc, char** argv) {
         else if (k == "--linear") cam.linear_name = argv[i + 1];
         else if (k == "--nee") cam.next_event_estimation = std::atoi(argv[i + 1]) != 0;
         else if (k == "--shadowed-point-lights") cam.shadowed_point_lights = std::atoi(argv[i + 1]) != 0;
+        else if (k == "--devices") {
+            std::string v = argv[i + 1];
+            cam.devices.clear();
+            if (v == "all") {
+                int n = rt_visible_devices();
+                for (int d = 0; d < n; d++) cam.devices.push_back(d);
+            } else {
+                size_t at = 0;
+                while (at < v.size()) {
+                    size_t c = v.find(',', at);
+                    if (c == std::string::npos) c = v.size();
+                    cam.devices.push_back(std::atoi(v.substr(at, c - at).c_str()));
+                    at = c + 1;
+                }
+            }
+        }
         else { std::cerr << "unknown option " << k << std::endl; return 1; }
     }
     cam.image_name = out.c_str();

@@ -9,16 +9,20 @@ default 16 steps are exactly the 1024-spp BASELINE frame).  Metric: Msamples/s (
   python bench.py --impl reference [...]                        the reference CPU renderer
 
 N > 1 is launched by torchrun, one process per GPU; the frame is tile-sharded (tile t -> rank
-t mod N), every rank renders into a full-frame int64 fixed-point buffer and ONE NCCL int64 SUM
-reduce to rank 0 (inside the timed region) finishes the frame: strong scaling, bit-identical
-image at any N.
+t mod N), every rank renders ONLY its tiles into a compact buffer (1/N of the frame,
+RT_FLAG_COMPACT_TILES), resolves them on its GPU and ONE NCCL gather of the resolved RGB8 tiles to
+rank 0 (inside the timed region) finishes the frame: strong scaling, bit-identical image at any N.
+(Frames with too few tiles shard the sample index and reduce full-frame int64 sums instead.)
 
 The JSON line carries, besides the contract keys: `roofline` (FP32 intersection roof, the
 binding one per SURVEY 8d; the FP32 peak is measured here with an FMA microbenchmark because
-MEASURED_PEAKS.json only holds HBM and bf16 numbers), `roofline_mem` (BVH-node + primitive
-bytes against the measured HBM copy bandwidth), `cpu_baseline` (the unmodified reference
-renderer timed on this box's host cores on a bounded sample) and `e2e` (host scene description
-in, host RGB8 frame out, through rt_upload_scene / rt_render / rt_download every step).
+MEASURED_PEAKS.json only holds HBM and bf16 numbers; `traffic` = DRAM bytes of one launch from the
+committed ncu capture beside the algorithmic frame bytes), `l1_bandwidth` (BVH-node + primitive
+bytes per second against an L1 load-bandwidth microbenchmark: the scene is cache-resident, so this
+is a cache figure, not an HBM one), `cpu_baseline` (the unmodified reference renderer timed on this
+box's host cores on a bounded sample) and `e2e` (host scene description in, host RGB8 frame out
+every step: rt_upload_scene + rt_render + the gathered, downloaded frame; the device-to-host copy
+of step i overlaps the render of step i + 1).
 """
 from __future__ import annotations
 
@@ -107,9 +111,11 @@ class ClockSampler:
 def cpu_reference_run(scene: str, width: int, height: int, spp: int, depth: int) -> dict:
     """One timed run of the reference CPU implementation on (width x height x spp).  Returns
     {value (Msamples/s), seconds, cores, kind, sample}."""
-    from raytracingoneweekendapplication_b200.assets import ensure_assets
+    assets = assets_dir()
+    if not os.path.exists(os.path.join(assets, "VERSION")):   # build() generates them; a pure-Python generator otherwise (no .so is loaded)
+        from raytracingoneweekendapplication_b200.assets import ensure_assets
 
-    assets = ensure_assets()
+        assets = ensure_assets()
     cores = os.cpu_count() or 1
     driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
     sample = f"{scene} {width}x{height} x {spp} spp, depth {depth}"
@@ -132,6 +138,24 @@ def cpu_reference_run(scene: str, width: int, height: int, spp: int, depth: int)
     return {"value": width * height * spp / dt * 1e-6, "unit": "Msamples/s", "seconds": dt, "cores": cores, "kind": "port", "sample": sample}
 
 
+BASELINE_FRAMES = {"final": (3840, 2160, 50), "book1": (400, 225, 50), "cornell": (600, 600, 50), "cornell_smoke": (600, 600, 50),
+                   "mesh": (1920, 1080, 50)}
+
+
+def assets_dir() -> str:
+    """The generated assets (textures, meshes) the scenes load; created by build() -- found without importing the package."""
+    return os.environ.get("RT_B200_ASSETS") or os.path.join(ROOT, "scenes", "assets")
+
+
+def reference_scene_info(scene: str) -> dict:
+    driver = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if os.path.exists(driver):
+        out = subprocess.check_output([driver, "scene", scene, "1", assets_dir()], stderr=subprocess.DEVNULL).decode()
+        return json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    w, h, d = BASELINE_FRAMES.get(scene, (1024, 576, 50))
+    return {"width": w, "height": h, "depth": d}
+
+
 def bounded_cpu_baseline(scene: str, width: int, height: int, depth: int, budget_s: float = 15.0) -> dict:
     """~10-30 s of CPU work on the same workload: one probe at a quarter-size frame, then the
     frame size that fits the budget at 1 spp (cost is linear in pixels x spp, Camera.txt:65-73)."""
@@ -148,11 +172,12 @@ def run_reference(args):
     """--impl reference: rank 0 times the reference CPU renderer; other ranks exit 0."""
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
-    from raytracingoneweekendapplication_b200 import capi
-
-    sc = capi.Scene(args.scene)
-    width, height = args.width or sc.width, args.height or sc.height
-    depth = args.depth or sc.depth
+    # frame size and depth of the BASELINE config from the reference driver itself (`ref_driver scene`): nothing of this
+    # repo's product (package, librt_b200.so) is imported or loaded on this arm
+    width, height, depth = args.width, args.height, args.depth
+    if not (width and height and depth):
+        info = reference_scene_info(args.scene)
+        width, height, depth = width or info["width"], height or info["height"], depth or info["depth"]
     # a bounded sample per step: the full frame would take minutes per step on a CPU
     probe = cpu_reference_run(args.scene, max(64, width // 8), max(36, height // 8), 1, depth)
     rate = max(probe["value"], 1e-6) * 1e6
@@ -167,7 +192,9 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(runs)), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{WORKLOADS.get(args.scene, args.scene)} {width}x{height}, depth {depth}",
-                   "scene": args.scene, "step": runs[0]["sample"] if runs else ""},
+                   "scene": args.scene, "width": width, "height": height, "depth": depth,
+                   "sample_width": w, "sample_height": h, "sample_spp": 1,
+                   "step": (runs[0]["sample"] if runs else "") + ": a bounded sample of the same camera and scene; Msamples/s does not depend on the frame size"},
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": runs[0]["cores"] if runs else 0,
                          "kind": runs[0]["kind"] if runs else "reference", "sample": runs[0]["sample"] if runs else ""},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -220,8 +247,25 @@ def run_b200(args):
     spp_step = args.spp_per_step
     ctx = capi.Context(local_rank)
     ctx.upload(sc)
-    accum = torch.zeros(width * height * 4, dtype=torch.int64, device="cuda")
-    ctx.bind_accum(accum.data_ptr(), accum.numel() * 8, width, height)
+    plan = sharding.plan(width, height, spp_step, rank, world, sharding.RT_SHARD_AUTO)
+    shard = dict(shard_rank=rank, shard_count=world, shard_mode=plan.mode)
+    # N > 1, tile-sharded: every rank owns 1/N of the tiles and renders them into a compact buffer inside the library;
+    # what travels is the resolved RGB8 of those tiles (3 bytes per pixel), gathered on rank 0.
+    # N > 1, sample-sharded (frames with too few tiles) and N = 1: a full-frame int64 buffer (a torch tensor bound with
+    # rt_bind_accum), summed over ranks with one int64 reduce.
+    compact = world > 1 and plan.mode == sharding.RT_SHARD_TILES
+    tile = 16
+    accum = g8 = g8_all = None
+    cap = 0
+    if compact:
+        cap = max(ctx.lib.rt_shard_pixels(width, height, tile, r, world) for r in range(world))
+        g8 = torch.zeros(cap * 3, dtype=torch.uint8, device="cuda")
+        g8_all = [torch.zeros(cap * 3, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+        shard["compact"] = True
+        shard["tile_size"] = tile
+    else:
+        accum = torch.zeros(width * height * 4, dtype=torch.int64, device="cuda")
+        ctx.bind_accum(accum.data_ptr(), accum.numel() * 8, width, height)
     # a non-default torch stream: its handle is what rt_render launches on (handle 0, the legacy
     # default stream, would read as "NULL = the context's own stream" in the C ABI), and the
     # torch.cuda.Events below are recorded on the same stream
@@ -229,8 +273,6 @@ def run_b200(args):
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
-    plan = sharding.plan(width, height, spp_step, rank, world, sharding.RT_SHARD_AUTO)
-    shard = dict(shard_rank=rank, shard_count=world, shard_mode=plan.mode)
 
     def barrier():
         if world > 1:
@@ -241,15 +283,24 @@ def run_b200(args):
         ctx.render(width, height, spp_step, max_depth=depth, seed=1, spp_begin=i * spp_step, accumulate=not first, stats=stats,
                    stream=stream, blocking=False, **shard)
 
+    def exchange(total_spp):
+        """The one exchange that finishes the frame on rank 0 (device-resident): resolved tiles gathered, or sums reduced."""
+        if world == 1:
+            return
+        if compact:
+            ctx.resolve_tiles(total_spp, g8.data_ptr(), cap)      # waits for this rank's passes, resolves its tiles on its GPU
+            dist.gather(g8, g8_all, dst=0)                        # NCCL over NVLink, on the current (torch) stream
+        else:
+            sharding.reduce_frame(accum)
+
     # ---- warm-up (untimed) ---------------------------------------------------------------
     for i in range(args.warmup):
         step(i, first=(i == 0))
-    if world > 1:
-        sharding.reduce_frame(accum.clone())
+    exchange(spp_step * max(1, args.warmup))
     barrier()
     ctx.sync()
 
-    # ---- timed region: exactly K steps + the one frame reduce ----------------------------------
+    # ---- timed region: exactly K steps + the one exchange ------------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -262,8 +313,8 @@ def run_b200(args):
         step(i, first=(i == 0))
         launches += 1
     ev_k.record()
-    if world > 1:
-        sharding.reduce_frame(accum)
+    exchange(spp_step * args.steps)
+    launches += 1 if compact else 0          # resolve_kernel over this rank's tiles
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -277,10 +328,17 @@ def run_b200(args):
     total_samples = width * height * spp_step * args.steps
     value = total_samples / (ms * 1e-3) * 1e-6
 
+    frame_out = None
     if rank == 0 and args.out_png:
+        if compact:
+            frame_out = ctx.untile(torch.stack(g8_all).data_ptr(), cap * 3, 3, world, width, height, tile)
+        elif world == 1:
+            frame_out = ctx.download(spp_step * args.steps, linear=False, rgb8=True)
+
+    if frame_out is not None:
         from raytracingoneweekendapplication_b200.host_png import write_png
 
-        write_png(args.out_png, ctx.download(spp_step * args.steps, linear=False, rgb8=True))
+        write_png(args.out_png, frame_out)
 
     # ---- per-launch algorithmic work (one counted pass of the same step, untimed) ---------------
     ctx.render(width, height, spp_step, max_depth=depth, seed=1, stats=True, **shard)   # blocking: fills counters
@@ -295,16 +353,11 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(counters, op=dist.ReduceOp.SUM)
     fp32_peak = ctx.measure_fp32_peak()
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    l1_peak = ctx.measure_l1_peak()
     # DRAM traffic of one launch, from the committed ncu capture of this very command/config
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         if tr.get("workload") == f"{args.scene} {width}x{height} {spp_step}spp" and world == 1:
             traffic = tr["traffic_bytes_per_launch"]
     except (OSError, ValueError, KeyError):
@@ -313,44 +366,65 @@ def run_b200(args):
     ach_gbs = (nbytes / (launch_ms * 1e-3)) * 1e-9
 
     # ---- e2e: host scene description in, host RGB8 frame out, every step ------------------------
+    # What camera::render does per frame, in a loop: rt_upload_scene (the flattened description; an unchanged scene is
+    # recognised by its fingerprint and only its staged arena is copied again), rt_render, and the frame handed out to
+    # host memory -- N = 1: rt_download_begin; N > 1: every rank resolves its tiles, NCCL gather to rank 0, rt_untile_begin
+    # there.  The device-to-host copy of step i runs on its own stream while step i + 1 renders; the loop ends when the
+    # last frame is in host memory.
     e2e = None
     if not args.no_e2e:
-        ctx.bind_accum(None, 0, 0, 0)
-        import numpy as np
-
-        frame8 = np.empty((height, width, 3), dtype=np.uint8)
+        if accum is not None:
+            ctx.bind_accum(None, 0, 0, 0)
         n_e2e = max(2, min(args.steps, 8))
-        # one untimed pass first: the library allocates its frame and output buffers on first use
-        ctx.upload(sc)
-        ctx.render(width, height, spp_step, max_depth=depth, seed=1, **shard)
+        g8_mat = torch.zeros((world, cap * 3), dtype=torch.uint8, device="cuda") if (compact and rank == 0) else None
+        g8_rows = list(g8_mat.unbind(0)) if g8_mat is not None else None
+        eshard = dict(shard)
+
+        def e2e_step(i):
+            ctx.upload(sc)                                                   # H2D: the scene
+            ctx.render(width, height, spp_step, max_depth=depth, seed=1, spp_begin=i * spp_step, blocking=False, **eshard)
+            if world == 1:
+                ctx.download_begin(spp_step, linear=False, rgb8=True)        # resolve + D2H queued behind the render
+            elif compact:
+                ctx.resolve_tiles(spp_step, g8.data_ptr(), cap)
+                dist.gather(g8, g8_rows, dst=0)
+                if rank == 0:
+                    torch.cuda.current_stream().synchronize()                # the gathered tiles are on this GPU
+                    ctx.untile_begin(g8_mat.data_ptr(), cap * 3, 3, world, width, height, tile)
+            else:
+                ctx.sync()
+                ptr, nb = ctx.accum_buffer()
+                sharding.reduce_frame(_as_tensor(ptr, nb))                   # sample-sharded: int64 sums over NCCL
+                torch.cuda.synchronize()
+                if rank == 0:
+                    ctx.download_begin(spp_step, linear=False, rgb8=True)
+
+        # one untimed step first: the library allocates its frame, output and pinned buffers on first use
+        e2e_step(0)
         if rank == 0:
-            ctx.lib.rt_download(ctx._h, spp_step, None, frame8.ctypes.data)
+            ctx.frame_end()
         barrier()
         t0 = time.perf_counter()
-        t_up = t_rd = t_dl = 0.0
+        checksum = 0
         for i in range(n_e2e):
-            ta = time.perf_counter()
-            ctx.upload(sc)                                                   # H2D: the flattened scene (+ host BVH build)
-            tb = time.perf_counter()
-            ctx.render(width, height, spp_step, max_depth=depth, seed=1, spp_begin=i * spp_step, **shard)
-            if world > 1:
-                ptr, nb = ctx.accum_buffer()
-                sharding.reduce_frame(_as_tensor(ptr, nb))                   # the library-owned buffer, over NCCL
-                torch.cuda.synchronize()
-            tc = time.perf_counter()
-            if rank == 0:
-                ctx.lib.rt_download(ctx._h, spp_step, None, frame8.ctypes.data)   # D2H: the RGB8 frame
-            td = time.perf_counter()
-            t_up += tb - ta; t_rd += tc - tb; t_dl += td - tc
+            e2e_step(i)
+            if rank == 0 and i > 0:
+                checksum += int(ctx.frame_end()[1][0, 0, 0])                 # frame i - 1 is in host memory
+        if rank == 0:
+            checksum += int(ctx.frame_end()[1][0, 0, 0])
+        ctx.sync()
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        stu = ctx.stats()
         e2e = {"value": width * height * spp_step * n_e2e / float(tt[0]) * 1e-6, "unit": "Msamples/s",
-               "h2d_bytes_per_step": scene_bytes(sc.desc), "d2h_bytes_per_step": width * height * 3, "steps": n_e2e,
-               "call": "rt_upload_scene + rt_render + rt_download(rgb8) per step (what camera::render does), host buffers",
-               "ms_upload": 1e3 * t_up / n_e2e, "ms_render": 1e3 * t_rd / n_e2e, "ms_download": 1e3 * t_dl / n_e2e}
+               "h2d_bytes_per_step": int(stu["upload_bytes"]), "d2h_bytes_per_step": width * height * 3, "steps": n_e2e,
+               "call": ("rt_upload_scene + rt_render + rt_download_begin / rt_frame_end per step" if world == 1 else
+                        "rt_upload_scene + rt_render(compact tiles) + rt_resolve_tiles + NCCL gather + rt_untile_begin / rt_frame_end per step"),
+               "ms_per_step": 1e3 * float(tt[0]) / n_e2e, "scene_description_bytes": scene_bytes(sc.desc),
+               "scene_reused": bool(stu["scene_reused"]), "overlap": "device-to-host copy of step i overlaps the render of step i + 1"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -368,9 +442,10 @@ def run_b200(args):
                 "workload": f"{WORKLOADS.get(args.scene, args.scene)} {width}x{height}, depth {depth}, {spp_step * args.steps} spp "
                             f"({spp_step} spp per step)",
                 "scene": args.scene, "width": width, "height": height, "spp_per_step": spp_step, "depth": depth,
-                "sharding": {1: "tiles 16x16 interleaved", 2: "samples interleaved"}[plan.mode] if world > 1 else "none",
-                "l2": "frame accumulation buffer %d MB > 126 MB L2 is re-read every step; the scene (~1 MB) is "
-                      "cache-resident by design" % (width * height * 32 // 2 ** 20),
+                "sharding": ({1: "tiles 16x16 interleaved, compact per-rank tile buffers, resolved RGB8 tiles gathered over NCCL",
+                              2: "samples interleaved, int64 sums reduced over NCCL"}[plan.mode]) if world > 1 else "none",
+                "l2": "frame accumulation buffer %d MB per rank%s is re-read every step; the scene (~1 MB) is "
+                      "cache-resident by design" % (32 * plan.pixels(width, height) // 2 ** 20, " (> 126 MB L2)" if 32 * plan.pixels(width, height) > 126 * 2 ** 20 else ""),
             },
             "mrays_per_s": float(counters[2]) / (launch_ms * 1e-3) * 1e-6,
             "rays_per_sample": float(counters[2]) / (width * height * spp_step),
@@ -379,11 +454,14 @@ def run_b200(args):
                          "peak_source": "measured here: FP32 FMA microbenchmark (rt_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
                          "algorithmic": "24/box + 30/sphere + 48/quad + 44/triangle + 40/boundary test + 50/ray shading (SURVEY 8d), "
                                         "counted on the device for this launch", "launch_ms": launch_ms, "per": "rank 0 launch"},
-            "roofline_mem": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                             "traffic": traffic, "algorithmic_bytes": nbytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+            "l1_bandwidth": {"bound": "l1", "achieved": ach_gbs, "peak": l1_peak, "unit": "GB/s", "frac": ach_gbs / l1_peak if l1_peak else None,
+                             "algorithmic_bytes": nbytes, "peak_source": "measured here: L1 128-bit load microbenchmark (rt_measure_l1_peak)",
                              "algorithmic": "64 B/node visit + 16/48/48 B per sphere/quad/triangle test + 16 B/ray shading fetch + "
-                                            "32 B/pixel accumulation", "note": "BVH and primitives are L1/L2 resident: this is a "
-                                            "cache-bandwidth figure reported against the HBM roof"},
+                                            "32 B/pixel accumulation",
+                             "note": "the BVH and the primitives are L1/L2 resident (L1 hit rate 90 %), so their bytes are cache traffic; the only "
+                                     "HBM traffic of a launch is the frame: see dram"},
+            "dram": {"algorithmic_frame_bytes": 32 * plan.pixels(width, height), "measured_bytes_per_launch": traffic,
+                     "source": "profiles/r2_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of the same command)" if traffic else None},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "device_stats": {k: st[k] for k in ("regs_per_thread", "blocks", "threads_per_block", "bvh_nodes", "bvh_depth", "nonfinite_samples",
                                                 "local_bytes_per_thread")},

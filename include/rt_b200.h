@@ -290,6 +290,10 @@ typedef struct rt_stats {
     /* multi-device contexts: devices of the context (counters above are summed over them, render_ms is the slowest
      * device's) and how rt_download gathers their tiles on device 0: 0 single device, 1 peer copies, 2 NCCL send/recv */
     uint32_t devices, gather_mode;
+    /* last rt_upload_scene: bytes copied to the device, and 1 when the scene was byte-identical to the one already
+     * uploaded (same builder settings), so that only the staged arena was copied again -- no validation, no BVH build */
+    uint64_t upload_bytes;
+    uint32_t scene_reused, reserved3_;
 } rt_stats;
 
 /* Create a context on the CUDA devices device_ids[0 .. n_devices).  With n_devices > 1 the context
@@ -301,6 +305,7 @@ typedef struct rt_stats {
  * rt_last_error works; destroy it. */
 int rt_create(rt_ctx** out, const int* device_ids, int n_devices);
 int rt_device_count(const rt_ctx* ctx);
+int rt_visible_devices(void); /* CUDA devices this process can see (0 without a driver); no context needed */
 void rt_destroy(rt_ctx* ctx);
 const char* rt_last_error(const rt_ctx* ctx);
 
@@ -392,6 +397,19 @@ int rt_resolve_tiles(rt_ctx* ctx, int32_t total_spp, float* dev_rgb_linear, uint
 int rt_untile(rt_ctx* ctx, const void* dev_shards, size_t shard_stride_bytes, int32_t bytes_per_pixel, int32_t shard_count,
               int32_t width, int32_t height, int32_t tile_size, void* host_out);
 
+/* Asynchronous hand-out of the frame: the copy to host memory overlaps the next pass.
+ *   rt_download_begin  like rt_download, but returns once the resolve and the device-to-host copy are QUEUED (the
+ *                      copy on a stream of its own, into pinned host memory owned by the context); the next
+ *                      rt_upload_scene / rt_render may be issued at once
+ *   rt_untile_begin    like rt_untile (bytes_per_pixel 3 or 12), same hand-out
+ *   rt_frame_end       waits for the OLDEST outstanding begin and returns pointers into the context's pinned
+ *                      buffer (NULL for a plane that was not asked for), valid until two more begins; at most two
+ *                      frames may be outstanding */
+int rt_download_begin(rt_ctx* ctx, int32_t total_spp, int32_t want_linear, int32_t want_rgb8);
+int rt_untile_begin(rt_ctx* ctx, const void* dev_shards, size_t shard_stride_bytes, int32_t bytes_per_pixel, int32_t shard_count,
+                    int32_t width, int32_t height, int32_t tile_size);
+int rt_frame_end(rt_ctx* ctx, const float** rgb_linear, const uint8_t** rgb8);
+
 int rt_get_stats(rt_ctx* ctx, rt_stats* out);
 
 /* sizeof() of the ABI structs as this library was compiled, so that a foreign-language
@@ -404,6 +422,9 @@ size_t rt_struct_size(int which);
 /* FP32 FMA issue-rate microbenchmark on the context's device, for the FP32
  * roofline denominator (not in MEASURED_PEAKS.json).  Returns TFLOP/s. */
 int rt_measure_fp32_peak(rt_ctx* ctx, double* tflops);
+/* L1 load-bandwidth microbenchmark (128-bit loads over an L1-resident window per block), GB/s: the denominator
+ * of the node/primitive-bytes figure -- the BASELINE scenes are cache-resident, their bytes are not HBM bytes. */
+int rt_measure_l1_peak(rt_ctx* ctx, double* gbs);
 
 /* Per-function device probes for known-answer tests: evaluate one hot-path
  * function on the device for n inputs (host pointers).

@@ -124,6 +124,7 @@ class rt_stats(C.Structure):
         ("bvh_width", C.c_uint32), ("wide_nodes", C.c_uint32), ("wide_depth", C.c_uint32), ("reserved2_", C.c_uint32),
         ("empty_node_steps", C.c_uint64),
         ("devices", C.c_uint32), ("gather_mode", C.c_uint32),
+        ("upload_bytes", C.c_uint64), ("scene_reused", C.c_uint32), ("reserved3_", C.c_uint32),
     ]
 
     def as_dict(self) -> dict:
@@ -135,6 +136,7 @@ EXPORTED_SYMBOLS = [
     "rt_accum_buffer", "rt_bind_accum", "rt_get_stats", "rt_measure_fp32_peak", "rt_probe_texture", "rt_probe_scatter",
     "rt_probe_hit", "rt_struct_size", "rt_accum_download", "rt_accum_upload", "rt_set_bvh_builder",
     "rt_set_bvh_width", "rt_device_count", "rt_shard_pixels", "rt_resolve_tiles", "rt_untile",
+    "rt_download_begin", "rt_untile_begin", "rt_frame_end", "rt_measure_l1_peak", "rt_visible_devices",
 ]
 
 ABI_STRUCTS = [rt_scene_desc, rt_render_params, rt_stats, rt_sphere, rt_quad, rt_triangle, rt_medium, rt_material, rt_texture,
@@ -190,9 +192,13 @@ def load() -> C.CDLL:
     lib.rt_shard_pixels.restype = C.c_size_t
     lib.rt_resolve_tiles.argtypes = [vp, i32, vp, vp, C.c_size_t]
     lib.rt_untile.argtypes = [vp, vp, C.c_size_t, i32, i32, i32, i32, i32, vp]
+    lib.rt_download_begin.argtypes = [vp, i32, i32, i32]
+    lib.rt_untile_begin.argtypes = [vp, vp, C.c_size_t, i32, i32, i32, i32, i32]
+    lib.rt_frame_end.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     lib.rt_accum_download.argtypes = [vp, vp, C.c_size_t]
     lib.rt_accum_upload.argtypes = [vp, vp, C.c_size_t, i32, i32]
     lib.rt_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.rt_measure_l1_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.rt_probe_texture.argtypes = [vp, i32, i32, vp, vp]
     lib.rt_probe_scatter.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.rt_probe_hit.argtypes = [vp, i32, vp, vp, vp, vp, vp]
@@ -396,6 +402,25 @@ class Context:
                                        out.ctypes.data))
         return out
 
+    def download_begin(self, total_spp: int, linear: bool = False, rgb8: bool = True) -> None:
+        """Queue resolve + device-to-host copy (pinned memory, own stream) and return; pair with frame_end()."""
+        self._check(self.lib.rt_download_begin(self._h, total_spp, int(linear), int(rgb8)))
+
+    def untile_begin(self, dev_shards: int, shard_stride_bytes: int, bytes_per_pixel: int, shard_count: int, width: int, height: int,
+                     tile_size: int = 16) -> None:
+        self._check(self.lib.rt_untile_begin(self._h, dev_shards, shard_stride_bytes, bytes_per_pixel, shard_count, width, height, tile_size))
+        self.width, self.height = width, height
+
+    def frame_end(self):
+        """(linear, rgb8) numpy VIEWS of the context's pinned buffer for the oldest outstanding begin (None for a plane
+        that was not asked for); valid until two more begins."""
+        lin, b8 = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.rt_frame_end(self._h, C.byref(lin), C.byref(b8)))
+        n = self.width * self.height * 3
+        a = np.ctypeslib.as_array((C.c_float * n).from_address(lin.value)).reshape(self.height, self.width, 3) if lin.value else None
+        b = np.ctypeslib.as_array((C.c_uint8 * n).from_address(b8.value)).reshape(self.height, self.width, 3) if b8.value else None
+        return a, b
+
     def accum_buffer(self):
         ptr, nbytes = C.c_void_p(), C.c_size_t()
         self._check(self.lib.rt_accum_buffer(self._h, C.byref(ptr), C.byref(nbytes)))
@@ -425,6 +450,11 @@ class Context:
     def measure_fp32_peak(self) -> float:
         v = C.c_double()
         self._check(self.lib.rt_measure_fp32_peak(self._h, C.byref(v)))
+        return v.value
+
+    def measure_l1_peak(self) -> float:
+        v = C.c_double()
+        self._check(self.lib.rt_measure_l1_peak(self._h, C.byref(v)))
         return v.value
 
     def probe_texture(self, texture: int, uvp: np.ndarray) -> np.ndarray:

@@ -152,6 +152,11 @@ extern "C" void rt_destroy(rt_ctx* ctx) {
 extern "C" const char* rt_last_error(const rt_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
 
 extern "C" int rt_device_count(const rt_ctx* ctx) { return ctx ? (int)ctx->dev.size() : 0; }
+extern "C" int rt_visible_devices(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 #define RT_NEED(ctx)                                        \
     if (!(ctx)) return RT_ERR_INVALID;                      \
@@ -468,6 +473,49 @@ extern "C" int rt_untile(rt_ctx* ctx, const void* dev_shards, size_t shard_strid
     return fwd(ctx, ctx->dev[0], dev_untile(ctx->dev[0], dev_shards, shard_stride_bytes, bytes_per_pixel, shard_count, width, height, tile_size, host_out));
 }
 
+// ---- asynchronous hand-out: the copy to (pinned) host memory overlaps the next pass ------------------------------------
+extern "C" int rt_download_begin(rt_ctx* ctx, int32_t total_spp, int32_t want_linear, int32_t want_rgb8) {
+    RT_NEED(ctx);
+    const int n = (int)ctx->dev.size();
+    if (n == 1) return fwd(ctx, ctx->dev[0], dev_download_begin(ctx->dev[0], total_spp, want_linear, want_rgb8));
+    // several devices: the gather is synchronous (it is microseconds over NVLink), the PCIe copy is what overlaps
+    if (!ctx->rendered) return failx(ctx, RT_ERR_STATE, "rt_download_begin: nothing rendered yet");
+    if (total_spp <= 0 || (!!want_linear == !!want_rgb8)) return failx(ctx, RT_ERR_INVALID, "rt_download_begin: a multi-device context hands out ONE of linear / rgb8 per call");
+    DevCtx* d0 = ctx->dev[0];
+    const int w = ctx->last.width, h = ctx->last.height;
+    if (!(d0->acc.compact && !ctx->base_sums && ctx->last.shard_count == n))
+        return failx(ctx, RT_ERR_UNSUPPORTED, "rt_download_begin: tile-sharded frames without a restored checkpoint only (use rt_download)");
+    const bool lin = want_linear != 0;
+    const size_t bpp = lin ? 12 : 3;
+    std::vector<const void*> src((size_t)n);
+    std::vector<size_t> bytes((size_t)n);
+    size_t stride = 0;
+    for (int d = 0; d < n; d++) {
+        DevCtx* dc = ctx->dev[d];
+        int rc = dev_wait(dc);
+        if (rc == RT_OK) rc = ensure_out(dc, dc->acc.slots());
+        // device 0's resolve output is also what its previous hand-out may still be copying from? no: hand-outs of a
+        // multi-device context copy from frame_scratch (the untiled frame), not from out_lin / out_rgb8
+        if (rc == RT_OK) rc = dev_resolve_into(dc, total_spp, lin ? dc->out_lin : nullptr, lin ? nullptr : dc->out_rgb8);
+        if (rc != RT_OK) return fwd(ctx, dc, rc);
+        src[d] = lin ? (const void*)dc->out_lin : (const void*)dc->out_rgb8;
+        bytes[d] = dc->acc.slots() * bpp;
+        stride = std::max(stride, (bytes[d] + 255) & ~(size_t)255);
+    }
+    int rc = gather_to_dev0(ctx, src, bytes, stride);
+    if (rc != RT_OK) return rc;
+    return fwd(ctx, d0, dev_untile_begin(d0, ctx->gather, stride, (int)bpp, n, w, h, ctx->last.tile_size));
+}
+extern "C" int rt_untile_begin(rt_ctx* ctx, const void* dev_shards, size_t shard_stride_bytes, int32_t bytes_per_pixel, int32_t shard_count,
+                               int32_t width, int32_t height, int32_t tile_size) {
+    RT_NEED(ctx);
+    return fwd(ctx, ctx->dev[0], dev_untile_begin(ctx->dev[0], dev_shards, shard_stride_bytes, bytes_per_pixel, shard_count, width, height, tile_size));
+}
+extern "C" int rt_frame_end(rt_ctx* ctx, const float** rgb_linear, const uint8_t** rgb8) {
+    RT_NEED(ctx);
+    return fwd(ctx, ctx->dev[0], dev_frame_end(ctx->dev[0], rgb_linear, rgb8));
+}
+
 extern "C" int rt_render_aov(rt_ctx* ctx, int32_t width, int32_t height, int32_t* prim_id, float* t, float* normal, float* point, float* uv) {
     RT_NEED(ctx);
     return fwd(ctx, ctx->dev[0], dev_render_aov(ctx->dev[0], width, height, prim_id, t, normal, point, uv));
@@ -505,6 +553,10 @@ extern "C" int rt_get_stats(rt_ctx* ctx, rt_stats* out) {
 extern "C" int rt_measure_fp32_peak(rt_ctx* ctx, double* tflops) {
     RT_NEED(ctx);
     return fwd(ctx, ctx->dev[0], dev_measure_fp32_peak(ctx->dev[0], tflops));
+}
+extern "C" int rt_measure_l1_peak(rt_ctx* ctx, double* gbs) {
+    RT_NEED(ctx);
+    return fwd(ctx, ctx->dev[0], dev_measure_l1_peak(ctx->dev[0], gbs));
 }
 extern "C" int rt_probe_texture(rt_ctx* ctx, int32_t texture, int32_t n, const float* uvp, float* rgb) {
     RT_NEED(ctx);

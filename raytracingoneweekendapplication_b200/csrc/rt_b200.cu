@@ -505,6 +505,32 @@ __global__ void fma_peak_kernel(float* out, int iters, float a, float b) {
     if (s == 12345.678f) out[0] = s;
 }
 
+// L1 load bandwidth: every warp streams 128-bit loads over a 32 KB window of its block (L1-resident after the
+// first sweep), four independent accumulators per thread.  The denominator of the node/primitive-bytes figure:
+// the BASELINE scenes live in L1/L2, so their bytes per second are a cache-bandwidth number, not an HBM one.
+__global__ void l1_peak_kernel(const uint4* __restrict__ buf, int iters, uint4* __restrict__ out) {
+    const uint4* base = buf + (size_t)blockIdx.x * 2048;  // 2048 x 16 B = 32 KB per block
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            // the window position moves with the iteration: loop-invariant addresses would be hoisted
+            const unsigned at = threadIdx.x + (unsigned)(8 * i + 4 * k) * 256u;
+            const uint4 v0 = __ldca(base + (at & 2047u));
+            const uint4 v1 = __ldca(base + ((at + 256u) & 2047u));
+            const uint4 v2 = __ldca(base + ((at + 512u) & 2047u));
+            const uint4 v3 = __ldca(base + ((at + 768u) & 2047u));
+            a0.x ^= v0.x; a0.y ^= v0.y; a0.z ^= v0.z; a0.w ^= v0.w;
+            a1.x ^= v1.x; a1.y ^= v1.y; a1.z ^= v1.z; a1.w ^= v1.w;
+            a2.x ^= v2.x; a2.y ^= v2.y; a2.z ^= v2.z; a2.w ^= v2.w;
+            a3.x ^= v3.x; a3.y ^= v3.y; a3.z ^= v3.z; a3.w ^= v3.w;
+        }
+        asm volatile("" ::: "memory");
+    }
+    const uint4 r = make_uint4(a0.x ^ a1.x ^ a2.x ^ a3.x, a0.y ^ a1.y ^ a2.y ^ a3.y, a0.z ^ a1.z ^ a2.z ^ a3.z, a0.w ^ a1.w ^ a2.w ^ a3.w);
+    if (r.x == 0x12345678u && r.y == 0x9abcdef0u) out[0] = r;
+}
+
 // ---------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------
@@ -572,6 +598,20 @@ struct DevCtx {
     int blocks_per_sm[2] = {0, 0};
     // acceleration structure the render kernels traverse: 2 = binary tree, 8 / 4 = wide quantised tree
     // (host-built scenes only; a device-built scene keeps the binary tree).  rt_set_bvh_width / RT_B200_BVH_WIDTH
+    // asynchronous frame hand-out (rt_download_begin / rt_untile_begin / rt_frame_end): the device-to-host copy runs on
+    // its own stream into pinned double buffers while the next pass renders
+    struct OutFrame {
+        cudaEvent_t done = nullptr;
+        unsigned char* pinned = nullptr;
+        size_t cap = 0, off_lin = 0, off_rgb8 = 0;
+        bool has_lin = false, has_rgb8 = false, active = false;
+    };
+    OutFrame frames[2];
+    int frame_head = 0, frames_out = 0;  // next slot to fill, outstanding begins
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_ready = nullptr;       // the device-side frame (resolved / untiled) is complete
+    uint64_t staged_key = 0;   // fingerprint of the scene whose arena image is in `staging` (0: none)
+    size_t staged_bytes = 0;
     int bvh_width = RT_B200_DEFAULT_BVH_WIDTH;
     int wide_depth = 0;  // levels of the uploaded wide tree = stack entries a ray can need
     bool pending_async = false;           // an RT_FLAG_ASYNC render has not been waited for yet (dev_wait)
@@ -734,6 +774,12 @@ static void dev_destroy(DevCtx* ctx) {
     if (ctx->dstats) cudaFree(ctx->dstats);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
+    for (auto& f : ctx->frames) {
+        if (f.done) cudaEventDestroy(f.done);
+        if (f.pinned) cudaFreeHost(f.pinned);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -768,7 +814,9 @@ bool texture_needs_uv(const rt_scene_desc* sc, int tex, int depth = 0) {
 
 }  // namespace
 
-static int validate_scene(DevCtx* ctx, const rt_scene_desc* sc) {
+// shallow: what must hold before the arrays may be read at all (the fingerprint of an unchanged scene is taken next);
+// the full pass checks every index
+static int validate_scene(DevCtx* ctx, const rt_scene_desc* sc, bool shallow) {
     if (!sc) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: null scene");
     if (sc->struct_size != sizeof(rt_scene_desc) || sc->abi_version != RT_B200_ABI_VERSION)
         return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: ABI mismatch (struct_size %u vs %zu, abi %u vs %d)", sc->struct_size,
@@ -778,7 +826,15 @@ static int validate_scene(DevCtx* ctx, const rt_scene_desc* sc) {
         neg(sc->n_media) || neg(sc->n_xforms) || neg(sc->n_materials) || neg(sc->n_textures) || neg(sc->n_images) ||
         neg(sc->n_perlins) || neg(sc->n_lights))
         return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: negative count");
-    if (sc->n_world + sc->n_boundary_refs >= (1 << 25)) return fail(ctx, RT_ERR_UNSUPPORTED, "rt_upload_scene: more than 2^25 primitives");
+    if ((long long)sc->n_world + sc->n_boundary_refs >= (1 << 25)) return fail(ctx, RT_ERR_UNSUPPORTED, "rt_upload_scene: more than 2^25 primitives");
+    // every array with a non-zero count must be there: nothing below dereferences a null pointer
+    if ((sc->n_world && !sc->world) || (sc->n_boundary_refs && !sc->boundary_refs) || (sc->n_spheres && !sc->spheres) || (sc->n_quads && !sc->quads) ||
+        (sc->n_triangles && !sc->triangles) || (sc->n_media && !sc->media) || (sc->n_xforms && !sc->xforms) || (sc->n_materials && !sc->materials) ||
+        (sc->n_textures && !sc->textures) || (sc->n_images && !sc->images) || (sc->n_perlins && !sc->perlins) || (sc->n_lights && !sc->lights))
+        return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: an array with a non-zero count is null");
+    // the free-flight uniforms of medium m come from Philox stream RS_MEDIUM + m / 4, which shares its counter word with
+    // the bounce number shifted by 8: more media than this would run into the bounce bits
+    if (sc->n_media > 4 * (256 - (int)RS_MEDIUM)) return fail(ctx, RT_ERR_UNSUPPORTED, "rt_upload_scene: at most %d media", 4 * (256 - (int)RS_MEDIUM));
     auto check_ref = [&](const rt_prim_ref& r, bool boundary) -> const char* {
         int n = r.type == RT_PRIM_SPHERE ? sc->n_spheres : r.type == RT_PRIM_QUAD ? sc->n_quads : r.type == RT_PRIM_TRIANGLE ? sc->n_triangles : -1;
         if (n < 0) return "unknown primitive type";
@@ -852,6 +908,50 @@ static int validate_scene(DevCtx* ctx, const rt_scene_desc* sc) {
     for (int i = 0; i < sc->n_images; i++)
         if (sc->images[i].width <= 0 || sc->images[i].height <= 0 || !sc->images[i].rgb) return fail(ctx, RT_ERR_INVALID, "rt_upload_scene: images[%d]: empty", i);
     return RT_OK;
+}
+
+// A 64-bit fingerprint of everything rt_upload_scene reads (the description, the arrays behind it, the texels) and
+// of the builder settings: an upload of the SAME scene (camera::render in a loop, progressive passes that re-upload)
+// skips validation, transform baking, the BVH build and the record derivation and only repeats the copy of the staged
+// arena to the device.  Word-wise multiply-xorshift (~5 GB/s); a collision would need 2^-64 luck.
+static uint64_t hash_bytes(uint64_t h, const void* data, size_t bytes) {
+    const unsigned char* p = (const unsigned char*)data;
+    const uint64_t k = 0x9E3779B97F4A7C15ull;
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+        uint64_t w;
+        std::memcpy(&w, p + i, 8);
+        h = (h ^ w) * k;
+        h ^= h >> 29;
+    }
+    uint64_t tail = 0;
+    if (i < bytes) std::memcpy(&tail, p + i, bytes - i);
+    h = (h ^ tail ^ ((uint64_t)bytes << 56)) * k;
+    return h ^ (h >> 32);
+}
+static uint64_t scene_key(const DevCtx* ctx, const rt_scene_desc* sc) {
+    uint64_t h = 0x1234567887654321ull;
+    const int32_t counts[16] = {sc->n_world, sc->n_boundary_refs, sc->n_spheres, sc->n_quads, sc->n_triangles, sc->n_media, sc->n_xforms, sc->n_materials,
+                                sc->n_textures, sc->n_images, sc->n_perlins, sc->n_lights, ctx->bvh_builder, ctx->bvh_width, RT_B200_ABI_VERSION, 0};
+    h = hash_bytes(h, counts, sizeof counts);
+    h = hash_bytes(h, &sc->camera, sizeof sc->camera);
+    h = hash_bytes(h, sc->world, (size_t)sc->n_world * sizeof(rt_prim_ref));
+    h = hash_bytes(h, sc->boundary_refs, (size_t)sc->n_boundary_refs * sizeof(rt_prim_ref));
+    h = hash_bytes(h, sc->spheres, (size_t)sc->n_spheres * sizeof(rt_sphere));
+    h = hash_bytes(h, sc->quads, (size_t)sc->n_quads * sizeof(rt_quad));
+    h = hash_bytes(h, sc->triangles, (size_t)sc->n_triangles * sizeof(rt_triangle));
+    h = hash_bytes(h, sc->media, (size_t)sc->n_media * sizeof(rt_medium));
+    h = hash_bytes(h, sc->xforms, (size_t)sc->n_xforms * sizeof(rt_xform));
+    h = hash_bytes(h, sc->materials, (size_t)sc->n_materials * sizeof(rt_material));
+    h = hash_bytes(h, sc->textures, (size_t)sc->n_textures * sizeof(rt_texture));
+    h = hash_bytes(h, sc->perlins, (size_t)sc->n_perlins * sizeof(rt_perlin));
+    h = hash_bytes(h, sc->lights, (size_t)sc->n_lights * sizeof(rt_point_light));
+    for (int i = 0; i < sc->n_images; i++) {
+        const int32_t wh[2] = {sc->images[i].width, sc->images[i].height};
+        h = hash_bytes(h, wh, sizeof wh);
+        if (sc->images[i].rgb && wh[0] > 0 && wh[1] > 0) h = hash_bytes(h, sc->images[i].rgb, (size_t)wh[0] * wh[1] * 3);
+    }
+    return h ? h : 1;
 }
 
 // Camera.txt:136-175 in double; stores the FP32 camera block for a width x height frame.
@@ -1185,6 +1285,8 @@ static int upload_scene_impl(DevCtx* ctx, const rt_scene_desc* sc, bool device_b
     if (!device_build) {
         CU(ctx, cudaMemcpyAsync(ctx->arena, ctx->staging, plan.size, cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->staged_bytes = plan.size;
+        ctx->stats.upload_bytes = plan.size;
     } else {
         for (int i = 0; i < sc->n_images; i++)
             CU(ctx, cudaMemcpyAsync(ctx->arena + img_off[i], ctx->staging + img_stage[i], (size_t)sc->images[i].width * sc->images[i].height * 3,
@@ -1255,11 +1357,26 @@ static int dev_wait(DevCtx* ctx);
 static int dev_upload_scene(DevCtx* ctx, const rt_scene_desc* sc) {
     if (!ctx) return RT_ERR_INVALID;
     auto t_begin = std::chrono::steady_clock::now();
-    int rc = validate_scene(ctx, sc);
+    int rc = validate_scene(ctx, sc, /*shallow=*/true);
     if (rc != RT_OK) return rc;
     CU(ctx, cudaSetDevice(ctx->device));
     // an asynchronous render may still be reading the arena -- on the caller's stream, not necessarily ours
     rc = dev_wait(ctx);
+    if (rc != RT_OK) return rc;
+    // the same scene again (same bytes, same builder settings): the staged arena is still in pinned memory -- copy it, done
+    const uint64_t key = getenv("RT_B200_NO_SCENE_CACHE") ? 0 : scene_key(ctx, sc);
+    if (key && ctx->has_scene && ctx->staged_key == key && ctx->staged_bytes > 0) {
+        CU(ctx, cudaMemcpyAsync(ctx->arena, ctx->staging, ctx->staged_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->stats.scene_reused = 1;
+        ctx->stats.upload_bytes = ctx->staged_bytes;
+        ctx->stats.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        return RT_OK;
+    }
+    ctx->staged_key = 0;
+    ctx->staged_bytes = 0;
+    ctx->stats.scene_reused = 0;
+    rc = validate_scene(ctx, sc, /*shallow=*/false);
     if (rc != RT_OK) return rc;
     free_scene(ctx);
     // which path: host (bake + binned SAH on the CPU) or device (csrc/bvh_device.cuh)
@@ -1268,6 +1385,7 @@ static int dev_upload_scene(DevCtx* ctx, const rt_scene_desc* sc) {
     bool too_deep = false;
     rc = upload_scene_impl(ctx, sc, device_build, &too_deep);
     if (rc == RT_OK && too_deep) rc = upload_scene_impl(ctx, sc, false, &too_deep);  // degenerate input: the SAH tree is shallow
+    if (rc == RT_OK && ctx->staged_bytes > 0) ctx->staged_key = key;  // host path: the whole arena sits in the pinned staging buffer
     if (rc == RT_OK) ctx->stats.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     return rc;
 }
@@ -1411,6 +1529,7 @@ static cudaError_t launch_untile(int bpp, const void* shards, size_t stride, int
 // device scratch that grows on demand (full-frame copies of compact data, gather staging)
 static int ensure_scratch_out(DevCtx* ctx, size_t bytes) {
     if (bytes <= ctx->frame_scratch_cap) return RT_OK;
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);  // an outstanding hand-out may still be copying from it
     if (ctx->frame_scratch) cudaFree(ctx->frame_scratch);
     ctx->frame_scratch = nullptr;
     ctx->frame_scratch_cap = 0;
@@ -1798,6 +1917,7 @@ static int dev_resolve_into(DevCtx* ctx, int32_t total_spp, float* dev_lin, unsi
 
 static int ensure_out(DevCtx* ctx, size_t pixels) {
     if (pixels <= ctx->out_pixels) return RT_OK;
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);  // an outstanding hand-out may still be copying from them
     if (ctx->out_lin) cudaFree(ctx->out_lin);
     if (ctx->out_rgb8) cudaFree(ctx->out_rgb8);
     ctx->out_lin = nullptr;
@@ -1838,6 +1958,97 @@ static int dev_untile(DevCtx* ctx, const void* dev_shards, size_t shard_stride_b
     CU(ctx, launch_untile(bytes_per_pixel, dev_shards, shard_stride_bytes, shard_count, -1, width, height, tile_size, ctx->frame_scratch, ctx->stream));
     CU(ctx, cudaMemcpyAsync(host_out, ctx->frame_scratch, full, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+// ---- asynchronous hand-out ---------------------------------------------------------------------------------------
+// begin: the frame is produced on ctx->stream (after whatever render is pending there or on the caller's stream), its
+// copy to pinned host memory is queued on ctx->copy_stream, the call returns.  end: waits for the OLDEST outstanding
+// begin and hands out pointers into the pinned buffer (valid until two more begins).  Two frames may be outstanding.
+static int frame_slot(DevCtx* ctx, size_t px, bool lin, bool rgb8, DevCtx::OutFrame** out) {
+    if (ctx->frames_out >= 2) return fail(ctx, RT_ERR_STATE, "two frames are already outstanding: call rt_frame_end first");
+    if (!ctx->copy_stream) CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->ev_ready) CU(ctx, cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
+    DevCtx::OutFrame& f = ctx->frames[ctx->frame_head];
+    if (!f.done) CU(ctx, cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+    const size_t need = (lin ? px * 12 : 0) + 256 + (rgb8 ? px * 3 : 0);
+    if (need > f.cap) {
+        if (f.pinned) cudaFreeHost(f.pinned);
+        f.pinned = nullptr;
+        f.cap = 0;
+        if (cudaHostAlloc(&f.pinned, need, cudaHostAllocDefault) != cudaSuccess) return fail(ctx, RT_ERR_NOMEM, "cannot allocate %zu bytes of pinned host memory", need);
+        f.cap = need;
+    }
+    f.has_lin = lin;
+    f.has_rgb8 = rgb8;
+    f.off_lin = 0;
+    f.off_rgb8 = lin ? ((px * 12 + 255) & ~(size_t)255) : 0;
+    *out = &f;
+    return RT_OK;
+}
+// the device buffers the previous begin copied from are about to be overwritten: its copy must be through
+static int frame_wait_prev_copy(DevCtx* ctx) {
+    const DevCtx::OutFrame& prev = ctx->frames[ctx->frame_head ^ 1];
+    if (prev.active) CU(ctx, cudaStreamWaitEvent(ctx->stream, prev.done, 0));
+    return RT_OK;
+}
+static int frame_queue_copy(DevCtx* ctx, DevCtx::OutFrame* f, const void* dev_lin, const void* dev_rgb8, size_t px) {
+    CU(ctx, cudaEventRecord(ctx->ev_ready, ctx->stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready, 0));
+    if (f->has_lin) CU(ctx, cudaMemcpyAsync(f->pinned + f->off_lin, dev_lin, px * 12, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (f->has_rgb8) CU(ctx, cudaMemcpyAsync(f->pinned + f->off_rgb8, dev_rgb8, px * 3, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CU(ctx, cudaEventRecord(f->done, ctx->copy_stream));
+    f->active = true;
+    ctx->frame_head ^= 1;
+    ctx->frames_out++;
+    return RT_OK;
+}
+
+static int dev_download_begin(DevCtx* ctx, int32_t total_spp, int32_t want_linear, int32_t want_rgb8) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (!ctx->accum) return fail(ctx, RT_ERR_STATE, "rt_download_begin: nothing rendered yet");
+    if (total_spp <= 0 || (!want_linear && !want_rgb8)) return fail(ctx, RT_ERR_INVALID, "rt_download_begin: bad arguments");
+    if (ctx->acc.compact) return fail(ctx, RT_ERR_UNSUPPORTED, "rt_download_begin: compact tile buffers go through rt_resolve_tiles / rt_untile_begin");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t px = ctx->acc.slots();
+    DevCtx::OutFrame* f = nullptr;
+    int rc = frame_slot(ctx, px, want_linear != 0, want_rgb8 != 0, &f);
+    if (rc == RT_OK) rc = ensure_out(ctx, px);
+    if (rc != RT_OK) return rc;
+    // stream order, no host wait: the pending render (on its own stream), then the previous copy, then the resolve
+    if (ctx->pending_async && ctx->pending_stream != ctx->stream) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev1, 0));
+    rc = frame_wait_prev_copy(ctx);
+    if (rc == RT_OK) rc = dev_resolve_into(ctx, total_spp, want_linear ? ctx->out_lin : nullptr, want_rgb8 ? ctx->out_rgb8 : nullptr);
+    if (rc != RT_OK) return rc;
+    return frame_queue_copy(ctx, f, ctx->out_lin, ctx->out_rgb8, px);
+}
+
+static int dev_untile_begin(DevCtx* ctx, const void* dev_shards, size_t shard_stride_bytes, int32_t bytes_per_pixel, int32_t shard_count, int32_t width,
+                            int32_t height, int32_t tile_size) {
+    if (!ctx || !dev_shards) return RT_ERR_INVALID;
+    if (width <= 0 || height <= 0 || tile_size <= 0 || shard_count <= 0 || (bytes_per_pixel != 3 && bytes_per_pixel != 12))
+        return fail(ctx, RT_ERR_INVALID, "rt_untile_begin: bad arguments (bytes_per_pixel 3 or 12)");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t px = (size_t)width * height;
+    DevCtx::OutFrame* f = nullptr;
+    int rc = frame_slot(ctx, px, bytes_per_pixel == 12, bytes_per_pixel == 3, &f);
+    if (rc == RT_OK) rc = ensure_scratch_out(ctx, px * bytes_per_pixel);
+    if (rc == RT_OK) rc = frame_wait_prev_copy(ctx);
+    if (rc != RT_OK) return rc;
+    CU(ctx, launch_untile(bytes_per_pixel, dev_shards, shard_stride_bytes, shard_count, -1, width, height, tile_size, ctx->frame_scratch, ctx->stream));
+    return frame_queue_copy(ctx, f, ctx->frame_scratch, ctx->frame_scratch, px);
+}
+
+static int dev_frame_end(DevCtx* ctx, const float** rgb_linear, const uint8_t** rgb8) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (ctx->frames_out <= 0) return fail(ctx, RT_ERR_STATE, "rt_frame_end: no frame is outstanding");
+    CU(ctx, cudaSetDevice(ctx->device));
+    DevCtx::OutFrame& f = ctx->frames[ctx->frames_out == 2 ? ctx->frame_head : (ctx->frame_head ^ 1)];
+    CU(ctx, cudaEventSynchronize(f.done));
+    f.active = false;
+    ctx->frames_out--;
+    if (rgb_linear) *rgb_linear = f.has_lin ? (const float*)(f.pinned + f.off_lin) : nullptr;
+    if (rgb8) *rgb8 = f.has_rgb8 ? (const uint8_t*)(f.pinned + f.off_rgb8) : nullptr;
     return RT_OK;
 }
 
@@ -1951,6 +2162,32 @@ static int dev_measure_fp32_peak(DevCtx* ctx, double* tflops) {
     }
     cudaFree(d);
     *tflops = best;
+    return RT_OK;
+}
+
+static int dev_measure_l1_peak(DevCtx* ctx, double* gbs) {
+    if (!ctx || !gbs) return RT_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 2, threads = 256, iters = 1 << 13;
+    uint4* d = nullptr;
+    const size_t bytes = (size_t)blocks * 2048 * sizeof(uint4);
+    CU(ctx, cudaMalloc(&d, bytes + 64));
+    cudaMemsetAsync(d, 1, bytes + 64, ctx->stream);
+    cudaFuncSetAttribute(l1_peak_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        l1_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters, d + (bytes / sizeof(uint4)));
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaError_t e = cudaEventSynchronize(ctx->ev1);
+        if (e != cudaSuccess) { cudaFree(d); return fail(ctx, RT_ERR_CUDA, "rt_measure_l1_peak: %s", cudaGetErrorString(e)); }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        const double moved = 16.0 * 8.0 * iters * (double)threads * blocks;
+        if (rep > 0) best = std::max(best, moved / (ms * 1e-3) * 1e-9);
+    }
+    cudaFree(d);
+    *gbs = best;
     return RT_OK;
 }
 

@@ -104,7 +104,8 @@ struct checkpoint_header {
     int32_t width, height;
     int32_t spp_done;      // samples [0, spp_done) of every pixel are in the sums
     int32_t max_depth;
-    uint32_t reserved;
+    uint32_t flags;        // estimator flags of the samples in the file (RT_FLAG_NEE, RT_FLAG_SHADOWED_POINT_LIGHTS): a render
+                           // with other flags is another integrand and must not continue from it
     uint64_t seed;
     uint64_t scene_hash;   // FNV-1a over the flattened scene description (0 = not checked)
 };
@@ -131,11 +132,15 @@ inline bool read_checkpoint(const char* path, checkpoint_header& hd, std::vector
     std::FILE* f = std::fopen(path, "rb");
     if (!f) return false;
     bool ok = std::fread(&hd, sizeof hd, 1, f) == 1 && std::memcmp(hd.magic, "RTB2CKPT", 8) == 0 && hd.version == 1 &&
-              hd.width > 0 && hd.height > 0 && hd.spp_done >= 0;
+              hd.width > 0 && hd.height > 0 && hd.spp_done >= 0 && (long long)hd.width * hd.height < (1ll << 31);
     if (ok) {
+        // the file must be exactly header + width * height * 32 bytes BEFORE anything is allocated from its header
         const size_t n = (size_t)hd.width * hd.height * 4;
-        sums.resize(n);
-        ok = std::fread(sums.data(), 8, n, f) == n && std::fgetc(f) == EOF;
+        ok = std::fseek(f, 0, SEEK_END) == 0 && (unsigned long long)std::ftell(f) == sizeof hd + 8ull * n && std::fseek(f, (long)sizeof hd, SEEK_SET) == 0;
+        if (ok) {
+            sums.resize(n);
+            ok = std::fread(sums.data(), 8, n, f) == n;
+        }
     }
     std::fclose(f);
     return ok;

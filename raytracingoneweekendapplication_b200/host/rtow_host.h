@@ -1532,8 +1532,11 @@ class camera {
     double defocus_angle = 0;
     double focus_dist = 10;
 
-    // additions (not in the reference): device, seed, and whether to write the PNG
+    // additions (not in the reference): device(s), seed, and whether to write the PNG.  `devices` non-empty: the frame is
+    // split over these GPUs of the box by ONE context (tile t -> devices[t mod n], tiles gathered over NVLink: replaces
+    // the row bands over CPU threads of Camera.txt:59-61, 96-100); the image does not depend on how many there are
     int device = 0;
+    std::vector<int> devices;
     uint64_t seed = 1;
     bool write_image = true;
     rt_stats last_stats{};
@@ -1580,13 +1583,13 @@ class camera {
         rt_scene_desc d = fs.desc();
 
         rt_ctx* ctx = nullptr;
-        int dev = device;
+        std::vector<int> devs = devices.empty() ? std::vector<int>{device} : devices;
         auto fail = [&](const char* what) {
             std::cerr << "\nrt_b200: " << what << " failed: " << (ctx ? rt_last_error(ctx) : "no context") << std::endl;
             if (ctx) rt_destroy(ctx);
             std::exit(2);
         };
-        if (rt_create(&ctx, &dev, 1) != RT_OK) fail("rt_create");
+        if (rt_create(&ctx, devs.data(), (int)devs.size()) != RT_OK) fail("rt_create");
         if (rt_upload_scene(ctx, &d) != RT_OK) fail("rt_upload_scene");
 
         rt_render_params p;
@@ -1604,17 +1607,25 @@ class camera {
         ck.version = 1;
         ck.width = p.width; ck.height = p.height; ck.max_depth = max_depth; ck.seed = seed;
         ck.scene_hash = checkpoint_path.empty() ? 0 : fs.hash();
+        const uint32_t estimator_flags = (next_event_estimation ? RT_FLAG_NEE : 0u) | (shadowed_point_lights ? RT_FLAG_SHADOWED_POINT_LIGHTS : 0u);
+        ck.flags = estimator_flags;
+        // a sample is clamped to 2^20 and stored in 2^-28 units: 2^16 samples of a saturated channel fill the 64-bit sum
+        if (samples_per_pixel > 65536) {
+            std::cerr << "rt_b200: samples_per_pixel " << samples_per_pixel << " exceeds 65536, the capacity of the 64-bit fixed-point sums" << std::endl;
+            if (ctx) rt_destroy(ctx);
+            std::exit(2);
+        }
         std::vector<uint64_t> sums;
         if (!checkpoint_path.empty()) {
             rtb200::checkpoint_header old;
             if (rtb200::read_checkpoint(checkpoint_path.c_str(), old, sums)) {
                 if (old.width == ck.width && old.height == ck.height && old.max_depth == ck.max_depth && old.seed == ck.seed &&
-                    old.scene_hash == ck.scene_hash && old.spp_done <= samples_per_pixel) {
+                    old.scene_hash == ck.scene_hash && old.flags == ck.flags && old.spp_done <= samples_per_pixel) {
                     if (rt_accum_upload(ctx, sums.data(), sums.size() * 8, p.width, p.height) != RT_OK) fail("rt_accum_upload");
                     done = old.spp_done;
                     std::cerr << "Resuming " << image_name << " at sample " << done << " from " << checkpoint_path << std::endl;
                 } else {
-                    std::cerr << "Ignoring " << checkpoint_path << ": it belongs to a different scene, frame, depth or seed" << std::endl;
+                    std::cerr << "Ignoring " << checkpoint_path << ": it belongs to a different scene, frame, depth, seed or estimator (NEE / shadowed lights)" << std::endl;
                 }
             }
         }
@@ -1636,8 +1647,7 @@ class camera {
             if (!checkpoint_path.empty() && checkpoint_every_spp > 0) n = std::min(n, std::max(1, checkpoint_every_spp - since_save));
             p.samples_per_pixel = n;
             p.spp_begin = done;
-            p.flags = (fresh ? 0 : RT_FLAG_ACCUMULATE) | (next_event_estimation ? RT_FLAG_NEE : 0) |
-                      (shadowed_point_lights ? RT_FLAG_SHADOWED_POINT_LIGHTS : 0);
+            p.flags = (fresh ? 0 : RT_FLAG_ACCUMULATE) | estimator_flags;
             fresh = false;
             if (rt_render(ctx, &p) != RT_OK) fail("rt_render");
             done += n;

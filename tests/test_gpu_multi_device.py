@@ -154,3 +154,80 @@ def test_nccl_and_peer_copy_gathers_agree(scene_of, monkeypatch):
             raise
     assert out["nccl"][3]["gather_mode"] == 2 and out["p2p"][3]["gather_mode"] == 1
     assert np.array_equal(out["nccl"][2], out["p2p"][2]) and np.array_equal(out["nccl"][0], out["p2p"][0])
+
+
+def test_asynchronous_hand_out_equals_the_blocking_download(scene_of):
+    """rt_download_begin / rt_frame_end: the copy runs behind the next pass; frames come back in order, equal to
+    rt_download's, and an unchanged scene is recognised on re-upload (only its staged arena is copied again)."""
+    sc = scene_of("cornell")
+    c = capi.Context(0)
+    try:
+        c.upload(sc)
+        assert c.stats()["scene_reused"] == 0 and c.stats()["upload_bytes"] > 0
+        want = []
+        for i in range(3):
+            c.render(160, 120, 2, max_depth=8, seed=3, spp_begin=2 * i)
+            want.append(c.download(2, linear=True, rgb8=True))
+        got = []
+        for i in range(3):
+            c.upload(sc)
+            assert c.stats()["scene_reused"] == 1
+            c.render(160, 120, 2, max_depth=8, seed=3, spp_begin=2 * i, blocking=False)
+            c.download_begin(2, linear=True, rgb8=True)
+            if i > 0:
+                lin, b8 = c.frame_end()
+                got.append((lin.copy(), b8.copy()))
+        lin, b8 = c.frame_end()
+        got.append((lin.copy(), b8.copy()))
+        for (wl, w8), (gl, g8) in zip(want, got):
+            assert np.array_equal(wl, gl) and np.array_equal(w8, g8)
+        with pytest.raises(capi.RtError):
+            c.frame_end()                      # nothing outstanding
+        # a changed scene is uploaded in full again
+        other = scene_of("quads")
+        c.upload(other)
+        assert c.stats()["scene_reused"] == 0
+    finally:
+        c.close()
+
+
+def test_multi_device_asynchronous_hand_out(scene_of, monkeypatch):
+    monkeypatch.setenv("RT_B200_ALLOW_DUPLICATE_DEVICES", "1")
+    sc = scene_of("final")
+    _, _, b8_ref = _reference(sc, 640, 360, 4, 10)
+    c = capi.Context([0, 0])
+    try:
+        c.upload(sc)
+        c.render(640, 360, 4, max_depth=10, seed=7)     # 920 tiles: tile-sharded
+        c.download_begin(4, linear=False, rgb8=True)
+        c.render(640, 360, 4, max_depth=10, seed=8)     # the next pass, while the first frame travels
+        _, b8 = c.frame_end()
+        assert np.array_equal(b8, b8_ref)
+    finally:
+        c.close()
+
+
+def test_cpp_host_program_splits_the_frame_over_devices(built, tmp_path, monkeypatch):
+    """apps/rtow_b200 ... --devices 0,0,0: main() -> camera::render(world, lights) with camera::devices set -> ONE context
+    over three "devices" -> the same PNG as on one device (a resumed render included)."""
+    import subprocess
+
+    import helpers
+    from raytracingoneweekendapplication_b200.assets import ensure_assets
+
+    exe = os.path.join(helpers.ROOT, "apps", "rtow_b200")
+    env = dict(os.environ, RT_B200_ALLOW_DUPLICATE_DEVICES="1")
+    one, many, resumed = (str(tmp_path / n) for n in ("one.png", "many.png", "resumed.png"))
+    ck = str(tmp_path / "ck.bin")
+    base = ["final", None, ensure_assets(), "640", "360", "6"]
+    for out, extra in ((one, []), (many, ["--devices", "0,0,0"])):
+        cmd = [exe] + [out if a is None else a for a in base] + extra
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stderr
+    assert open(one, "rb").read() == open(many, "rb").read()
+    for extra in (["--stop-after", "2"], []):
+        cmd = [exe] + [resumed if a is None else a for a in base] + ["--devices", "0,0", "--checkpoint", ck] + extra
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stderr
+    assert "Resuming" in r.stderr
+    assert open(one, "rb").read() == open(resumed, "rb").read()
