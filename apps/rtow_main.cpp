@@ -2,6 +2,10 @@
 // the B200 path underneath: the same include list, the same scene-construction code
 // (scenes.h), the same `cam.render(world, lights)` call.  The Win32 shell glue of the
 // reference (file dialogs, ShellExecuteW) is out of scope.
+#ifdef RTB200_USE_STB_IMAGE
+#define STB_IMAGE_IMPLEMENTATION
+#include "stb_image.h"
+#endif
 #include "rtweekend.h"
 
 #include "bvh.h"

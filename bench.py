@@ -380,17 +380,29 @@ def run_b200(args):
         g8_rows = list(g8_mat.unbind(0)) if g8_mat is not None else None
         eshard = dict(shard)
 
+        parts = {"upload": 0.0, "render": 0.0, "exchange": 0.0, "hand_out": 0.0}
+
         def e2e_step(i):
+            ta = time.perf_counter()
             ctx.upload(sc)                                                   # H2D: the scene
+            tb = time.perf_counter()
             ctx.render(width, height, spp_step, max_depth=depth, seed=1, spp_begin=i * spp_step, blocking=False, **eshard)
             if world == 1:
                 ctx.download_begin(spp_step, linear=False, rgb8=True)        # resolve + D2H queued behind the render
+                parts["upload"] += tb - ta
+                parts["hand_out"] += time.perf_counter() - tb
             elif compact:
-                ctx.resolve_tiles(spp_step, g8.data_ptr(), cap)
+                ctx.resolve_tiles(spp_step, g8.data_ptr(), cap)              # returns when this rank's pass is done and resolved
+                tc = time.perf_counter()
                 dist.gather(g8, g8_rows, dst=0)
+                torch.cuda.current_stream().synchronize()                    # rank 0: the gathered tiles are on its GPU
+                td = time.perf_counter()
                 if rank == 0:
-                    torch.cuda.current_stream().synchronize()                # the gathered tiles are on this GPU
                     ctx.untile_begin(g8_mat.data_ptr(), cap * 3, 3, world, width, height, tile)
+                parts["upload"] += tb - ta
+                parts["render"] += tc - tb
+                parts["exchange"] += td - tc
+                parts["hand_out"] += time.perf_counter() - td
             else:
                 ctx.sync()
                 ptr, nb = ctx.accum_buffer()
@@ -424,7 +436,8 @@ def run_b200(args):
                "call": ("rt_upload_scene + rt_render + rt_download_begin / rt_frame_end per step" if world == 1 else
                         "rt_upload_scene + rt_render(compact tiles) + rt_resolve_tiles + NCCL gather + rt_untile_begin / rt_frame_end per step"),
                "ms_per_step": 1e3 * float(tt[0]) / n_e2e, "scene_description_bytes": scene_bytes(sc.desc),
-               "scene_reused": bool(stu["scene_reused"]), "overlap": "device-to-host copy of step i overlaps the render of step i + 1"}
+               "scene_reused": bool(stu["scene_reused"]), "overlap": "device-to-host copy of step i overlaps the render of step i + 1",
+               "host_ms_per_step_rank0": {k: 1e3 * v / (n_e2e + 1) for k, v in parts.items()}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -427,7 +427,8 @@ int rt_measure_fp32_peak(rt_ctx* ctx, double* tflops);
 int rt_measure_l1_peak(rt_ctx* ctx, double* gbs);
 
 /* Per-function device probes for known-answer tests: evaluate one hot-path
- * function on the device for n inputs (host pointers).
+ * function on the device for n inputs (host pointers).  `texture` / `material` are indices into the uploaded
+ * tables; an index outside them is RT_ERR_INVALID.
  *   rt_probe_texture: texture::value (texture.h) for n (u,v,p) tuples.
  *   rt_probe_scatter: material::emitted + material::scatter (material.h) with the
  *     four uniforms the bounce would have drawn supplied by the caller:
@@ -437,9 +438,11 @@ int rt_measure_l1_peak(rt_ctx* ctx, double* gbs);
 int rt_probe_texture(rt_ctx* ctx, int32_t texture, int32_t n,
                      const float* uvp /* n*5: u v px py pz */, float* rgb /* n*3 */);
 int rt_probe_scatter(rt_ctx* ctx, int32_t material, int32_t n,
-                     const float* in /* n*16: o[3] d[3] time p[3] normal[3] front u v pad */,
+                     const float* in /* n*16: o[3] d[3] time p[3] normal[3] front u v */,
                      const float* uniforms /* n*4 */,
-                     float* out /* n*12: scattered att[3] o[3] d[3] pad emit[3]... see DESIGN.md */);
+                     float* out /* n*16 floats, 64 bytes per record: [0] scattered (1/0), [1..3] attenuation,
+                                   [4..6] scattered origin, [7..9] scattered direction, [10..12] emitted,
+                                   [13] scattered time, [14..15] zero */);
 int rt_probe_hit(rt_ctx* ctx, int32_t n, const float* rays /* n*9: o[3] d[3] time tmin tmax */,
                  int32_t* prim_id, float* t, float* normal, float* uv);
 

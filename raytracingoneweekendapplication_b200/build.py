@@ -45,10 +45,31 @@ def build_cuda(force: bool = False, verbose_ptxas: bool = False, alt_kernels: bo
     return out
 
 
+REFERENCE = "/root/reference"
+
+
+def ensure_reference_assets() -> str | None:
+    """Where the reference tree is mounted, its two shipped inputs (monkey.obj, Images/earthmap.jpg: BASELINE
+    configs[3] / configs[4]) are copied into the git-ignored scenes/assets/reference/ so that the `monkey` scene can be
+    built by both header sets and travels to the GPU box like the other built artefacts.  Never committed."""
+    dst = os.path.join(ROOT, "scenes", "assets", "reference")
+    pairs = [(os.path.join(REFERENCE, "monkey.obj"), "monkey.obj"), (os.path.join(REFERENCE, "Images", "earthmap.jpg"), "earthmap.jpg")]
+    if all(os.path.exists(s) for s, _ in pairs):
+        os.makedirs(dst, exist_ok=True)
+        for src, name in pairs:
+            if _newer(os.path.join(dst, name), [src]):
+                shutil.copyfile(src, os.path.join(dst, name))
+    return dst if all(os.path.exists(os.path.join(dst, n)) for _, n in pairs) else None
+
+
 def build_host(force: bool = False) -> str:
     out = os.path.join(PKG, "libscenes_b200.so")
     host = os.path.join(PKG, "host")
     inc = ["-I" + os.path.join(ROOT, "include"), "-I" + host, "-I" + os.path.join(ROOT, "scenes")]
+    # JPEG textures are decoded by the USER'S stb_image.h (host I/O outside the hot path): available where the
+    # reference tree is mounted; elsewhere the prebuilt library travels, or the mirror reads PPM only
+    if os.path.exists(os.path.join(REFERENCE, "stb_image.h")):
+        inc += ["-DRTB200_USE_STB_IMAGE", "-idirafter", REFERENCE]
     srcs = [os.path.join(host, "rtow_host.h"), os.path.join(host, "png_write.h"), os.path.join(host, "frame_io.h"), os.path.join(host, "host_rng.h"),
             os.path.join(ROOT, "scenes", "scenes.h"), os.path.join(ROOT, "scenes", "scenes_capi.cpp"),
             os.path.join(ROOT, "include", "rt_b200.h")]
@@ -74,6 +95,7 @@ def build_all(force: bool = False, alt_kernels: bool = False) -> None:
     from .assets import ensure_assets
 
     ensure_assets()
+    ensure_reference_assets()
 
 
 if __name__ == "__main__":

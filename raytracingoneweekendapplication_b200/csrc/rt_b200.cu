@@ -610,6 +610,7 @@ struct DevCtx {
     int frame_head = 0, frames_out = 0;  // next slot to fill, outstanding begins
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_ready = nullptr;       // the device-side frame (resolved / untiled) is complete
+    int n_materials = 0, n_textures = 0;  // sizes of the uploaded tables (the probes check their indices)
     uint64_t staged_key = 0;   // fingerprint of the scene whose arena image is in `staging` (0: none)
     size_t staged_bytes = 0;
     int bvh_width = RT_B200_DEFAULT_BVH_WIDTH;
@@ -1095,8 +1096,14 @@ static int upload_scene_impl(DevCtx* ctx, const rt_scene_desc* sc, bool device_b
     // world list); the kernels that write the quad records look the light number up by source index
     std::vector<int32_t> quad_light;
     if (device_build) {
+        // only quads the WORLD list references can be hit, so only those are emitters to sample: a quad that is just
+        // the boundary of a medium, or that nothing references, would add radiance the reference does not have
+        std::vector<char> in_world((size_t)sc->n_quads, 0);
+        for (int i = 0; i < sc->n_world; i++)
+            if (sc->world[i].type == RT_PRIM_QUAD) in_world[(size_t)sc->world[i].index] = 1;
         for (int i = 0; i < sc->n_quads; i++) {
             const rt_quad& q = sc->quads[i];
+            if (!in_world[(size_t)i]) continue;
             if (q.material < 0 || q.material >= sc->n_materials) continue;
             const rt_material& m = sc->materials[q.material];
             if (m.type != RT_MAT_DIFFUSE_LIGHT && m.type != RT_MAT_EMISSIVE_LIGHT) continue;
@@ -1342,6 +1349,8 @@ static int upload_scene_impl(DevCtx* ctx, const rt_scene_desc* sc, bool device_b
     ctx->stats.wide_nodes = wide.n_nodes;
     ctx->stats.wide_depth = wide.depth;
     ctx->camera = sc->camera;
+    ctx->n_materials = sc->n_materials;
+    ctx->n_textures = sc->n_textures;
     ctx->scene_lite = tri.empty() && world_count[PT_TRI] == 0 && sc->n_lights == 0 && !(sc->camera.defocus_angle > 0);
     ctx->cam_w = ctx->cam_h = 0;
     ctx->has_scene = true;
@@ -2224,6 +2233,7 @@ static int dev_probe_texture(DevCtx* ctx, int32_t texture, int32_t n, const floa
     if (!ctx) return RT_ERR_INVALID;
     if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "rt_probe_texture: no scene uploaded");
     if (n <= 0 || !uvp || !rgb) return fail(ctx, RT_ERR_INVALID, "rt_probe_texture: bad arguments");
+    if (texture < 0 || texture >= ctx->n_textures) return fail(ctx, RT_ERR_INVALID, "rt_probe_texture: texture %d outside [0,%d)", texture, ctx->n_textures);
     return run_probe(ctx, "rt_probe_texture", {{uvp, (size_t)n * 20}}, {{rgb, (size_t)n * 12}},
                      [&](std::vector<void*>& in, std::vector<void*>& out) {
                          probe_texture_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, texture, n, (const float*)in[0], (float*)out[0]);
@@ -2234,6 +2244,7 @@ static int dev_probe_scatter(DevCtx* ctx, int32_t material, int32_t n, const flo
     if (!ctx) return RT_ERR_INVALID;
     if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "rt_probe_scatter: no scene uploaded");
     if (n <= 0 || !in_rec || !uniforms || !out_rec) return fail(ctx, RT_ERR_INVALID, "rt_probe_scatter: bad arguments");
+    if (material < 0 || material >= ctx->n_materials) return fail(ctx, RT_ERR_INVALID, "rt_probe_scatter: material %d outside [0,%d)", material, ctx->n_materials);
     return run_probe(ctx, "rt_probe_scatter", {{in_rec, (size_t)n * 64}, {uniforms, (size_t)n * 16}}, {{out_rec, (size_t)n * 64}},
                      [&](std::vector<void*>& in, std::vector<void*>& out) {
                          probe_scatter_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, material, n, (const float*)in[0],

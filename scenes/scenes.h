@@ -315,6 +315,36 @@ inline void specular_scene(hittable_list& world, camera& cam, scene_config& cfg)
     cam.defocus_angle = 0;
 }
 
+// The reference's OWN inputs (BASELINE configs[3], configs[4]): monkey.obj through mesh::loadObj (32 triangular and
+// 468 quad faces -> 968 triangles; both halves of a quad take the UVs of its first three corners, mesh.h:78-81) under
+// the transform of main.cpp:399-405 (translate * rotate_y(90) * scale 1.5), textured with Images/earthmap.jpg decoded by
+// stb_image and linearised by rtw_image (rtw_stb_image.h:99-121), an earth globe with the same texture (main.cpp:166-167)
+// and one point light.  The two files are copied from the reference tree into <asset_dir>/reference/ by the build where
+// that tree is mounted (build.ensure_reference_assets); nothing else needs them.
+inline void monkey_scene(hittable_list& world, camera& cam, std::vector<point_light>& lights, scene_config& cfg) {
+    world.add(make_shared<sphere>(point3(0, -1000, 0), 1000, make_shared<lambertian>(color(0.4, 0.4, 0.4))));
+    auto earth_texture = make_shared<image_texture>((cfg.asset_dir + "/reference/earthmap.jpg").c_str());
+    auto earth_mat = make_shared<lambertian>(earth_texture);
+    {
+        mesh monkey;
+        glm::mat4 tf = glm::mat4(1.0f);
+        tf = glm::translate(tf, glm::vec3(3, 1.5f, 0));
+        tf = glm::rotate(tf, glm::radians(90.0f), glm::vec3(0, 1, 0));
+        tf = glm::scale(tf, glm::vec3(1.5f, 1.5f, 1.5f));
+        monkey.loadObj(cfg.asset_dir + "/reference/monkey.obj", world, earth_mat, tf);
+    }
+    world.add(make_shared<sphere>(point3(3, 1.2, 3.6), 1.2, earth_mat));
+    world.add(make_shared<sphere>(point3(3, 0.8, -3.2), 0.8, make_shared<metal>(color(0.8, 0.8, 0.9), 0.05)));
+    lights.push_back(point_light(point3(-6, 8, 2), color(30, 30, 28), 0.5));
+    set_frame(cam, cfg, 1920, 1080, 64);
+    cam.background = color(0.55, 0.65, 0.85);
+    cam.vfov = 30;
+    cam.lookfrom = point3(-9, 4, 1.5);
+    cam.lookat = point3(3, 1.3, 0.2);
+    cam.vup = vec3(0, 1, 0);
+    cam.defocus_angle = 0;
+}
+
 // main.cpp:128-175 (scene 0): checker ground, dielectric, Perlin sphere, a UV-checkered
 // triangle, an image-textured globe, slight defocus
 inline void mixed(hittable_list& world, camera& cam, scene_config& cfg) {
@@ -404,6 +434,7 @@ inline bool build_scene(const std::string& name, unsigned seed, hittable_list& w
     else if (name == "specular") specular_scene(world, cam, cfg);
     else if (name == "mixed") mixed(world, cam, cfg);
     else if (name == "kitchen_sink") kitchen_sink(world, cam, lights, cfg);
+    else if (name == "monkey") monkey_scene(world, cam, lights, cfg);
     else return false;
     if (cfg.wrap_in_bvh) world = hittable_list(make_shared<bvh_node>(world));
     return true;

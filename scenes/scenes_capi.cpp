@@ -2,6 +2,12 @@
 // reference's scene API and hands the flattened description to callers that are not C++
 // (the pytest suite and bench.py, via ctypes).  Links against librt_b200.so because the
 // mirror's camera::render calls the C ABI.
+#ifdef RTB200_USE_STB_IMAGE
+// JPEG / PNG textures decoded the way the reference decodes them: the user's own stb_image.h (the build adds the
+// reference tree to the include path where it is mounted; stb_image is third-party I/O, outside the hot path)
+#define STB_IMAGE_IMPLEMENTATION
+#include "stb_image.h"
+#endif
 #include "rtow_host.h"
 
 #include "scenes.h"
@@ -148,5 +154,13 @@ rtsc_scene* rtsc_load_obj(const char* path, int per_triangle, int with_media, fl
 int rtsc_write_exr(const char* path, int w, int h, const float* rgb) { return rtb200::write_exr(path, w, h, rgb) ? 0 : 1; }
 int rtsc_write_pfm(const char* path, int w, int h, const float* rgb) { return rtb200::write_pfm(path, w, h, rgb) ? 0 : 1; }
 uint64_t rtsc_scene_hash(const rtsc_scene* s) { return s ? s->fs.hash() : 0; }
+// 1 when this library decodes JPEG / PNG textures (built with the user's stb_image.h), 0 when only PPM / PGM
+int rtsc_has_stb() {
+#ifdef RTB200_USE_STB_IMAGE
+    return 1;
+#else
+    return 0;
+#endif
+}
 
 }  // extern "C"

@@ -10,7 +10,7 @@ oracle/Makefile) in this container and stores, per scene:
                         with scripted uniforms
   image_<scene>.npz     a converged float radiance image (linear, before gamma) + its spp
 
-Usage:  python tests/golden/make_golden.py [primary] [kat] [image] [--scenes a,b,c]
+Usage:  python tests/golden/make_golden.py [primary] [kat] [image] [image_quarter] [--scenes a,b,c]
 The fixtures are committed; /root/reference is not needed to run the tests.
 """
 from __future__ import annotations
@@ -35,13 +35,17 @@ SEED = 1
 PRIMARY = {
     "book1": (200, 112), "cornell": (150, 150), "cornell_smoke": (150, 150), "mesh": (240, 135), "final": (240, 135),
     "quads": (100, 100), "emissive": (100, 56), "specular": (128, 72), "mixed": (128, 72), "kitchen_sink": (160, 90),
+    # the reference's own inputs (monkey.obj, Images/earthmap.jpg): needs the reference tree (build.ensure_reference_assets)
+    "monkey": (240, 135),
 }
 IMAGE = {
     "book1": (120, 68, 4096), "cornell": (64, 64, 32768), "cornell_smoke": (64, 64, 32768), "mesh": (128, 72, 2048),
     "final": (96, 54, 65536), "quads": (64, 64, 2048), "emissive": (64, 36, 2048), "specular": (96, 54, 4096),
-    "mixed": (96, 54, 4096), "kitchen_sink": (96, 54, 4096),
+    "mixed": (96, 54, 4096), "kitchen_sink": (96, 54, 4096), "monkey": (128, 72, 4096),
 }
-KAT = {"kitchen_sink": 600, "mixed": 400, "final": 400, "book1": 400, "specular": 200, "mesh": 300}
+# C1-C3 once more at a QUARTER of the BASELINE frame (half the width, half the height), same gate
+IMAGE_QUARTER = {"book1": (200, 112, 8192), "cornell": (300, 300, 32768), "cornell_smoke": (300, 300, 32768)}
+KAT = {"kitchen_sink": 600, "mixed": 400, "final": 400, "book1": 400, "specular": 200, "mesh": 300, "monkey": 600}
 
 
 def run(*args) -> dict:
@@ -81,8 +85,10 @@ def main(argv):
                 leaves = np.fromfile(prefix + ".leaves.f64", dtype=np.float64).reshape(-1, 10)
                 np.savez_compressed(os.path.join(OUT, f"kat_{name}.npz"), kat=kat, leaves=leaves, seed=SEED)
                 print("kat", name, info["cases"], flush=True)
-        if "image" in what:
-            for name, (w, h, spp) in IMAGE.items():
+        jobs = [(name, v, f"image_{name}.npz") for name, v in IMAGE.items()] if "image" in what else []
+        jobs += [(name, v, f"image_{name}_quarter.npz") for name, v in IMAGE_QUARTER.items()] if "image_quarter" in what else []
+        if jobs:
+            for name, (w, h, spp), out_name in jobs:
                 if scenes and name not in scenes:
                     continue
                 path = os.path.join(tmp, "i_" + name + ".f32")
@@ -90,7 +96,7 @@ def main(argv):
                 info = run("render", name, SEED, assets, w, h, spp, depth, path)
                 img = np.fromfile(path, dtype=np.float32).reshape(info["height"], w, 3)
                 var = np.fromfile(path + ".var", dtype=np.float32).reshape(info["height"], w, 3)
-                np.savez_compressed(os.path.join(OUT, f"image_{name}.npz"), image=img, var=var, spp=spp, depth=depth, seed=SEED)
+                np.savez_compressed(os.path.join(OUT, out_name), image=img, var=var, spp=spp, depth=depth, seed=SEED)
                 print("image", name, w, info["height"], spp, "%.1fs" % info["seconds"], "mean", img.mean(axis=(0, 1)), flush=True)
 
 

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 from raytracingoneweekendapplication_b200 import capi  # noqa: E402
 
 
-@pytest.mark.parametrize("name", ["kitchen_sink", "mixed", "final", "book1", "specular", "mesh"])
+@pytest.mark.parametrize("name", ["kitchen_sink", "mixed", "final", "book1", "specular", "mesh", "monkey"])
 def test_scatter_matches_reference_known_answers(ctx, scene_of, name):
     from oracle import port
 
@@ -65,7 +65,7 @@ def _uses_noise(d, m):
     return False
 
 
-@pytest.mark.parametrize("name", ["kitchen_sink", "mixed", "final"])
+@pytest.mark.parametrize("name", ["kitchen_sink", "mixed", "final", "monkey"])
 def test_every_texture_matches_oracle_on_random_points(ctx, scene_of, name):
     """texture::value for every texture of the scene: solid, nested checker, UV checker, image
     (nearest texel on the gamma-linearised bytes), Perlin marble."""

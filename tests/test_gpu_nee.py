@@ -176,3 +176,55 @@ def test_nee_is_the_same_with_the_device_built_scene(scene_of):
     assert np.array_equal(frames[0], frames[2])
     assert np.array_equal(frames[1], frames[3])
     assert not np.array_equal(frames[0], frames[1])
+
+
+def test_nee_lists_only_emitters_the_world_references():
+    """An emissive quad that is not in the world list (the boundary of a medium, or referenced by nothing) can never be
+    hit by a path, so it must not be sampled as an emitter either -- on the host-built and on the device-built scene
+    alike (the device path reads the source quad array, the host path the world order)."""
+    import ctypes as C
+
+    import fuzz_scenes
+
+    base = fuzz_scenes.random_scene(3, 12, 8, 0, with_xforms=False)
+    d = base.desc
+    # two extra quads: the world light, and a huge bright emissive quad that nothing references
+    nq = d.n_quads
+    quads = (capi.rt_quad * (nq + 2))()
+    for i in range(nq):
+        quads[i] = d.quads[i]
+    mats = (capi.rt_material * (d.n_materials + 1))()
+    for i in range(d.n_materials):
+        mats[i] = d.materials[i]
+    texs = (capi.rt_texture * (d.n_textures + 1))()
+    for i in range(d.n_textures):
+        texs[i] = d.textures[i]
+    texs[d.n_textures].type = capi.RT_TEX_SOLID
+    texs[d.n_textures].color[:] = [30.0, 30.0, 30.0]
+    mats[d.n_materials].type, mats[d.n_materials].texture = capi.RT_MAT_DIFFUSE_LIGHT, d.n_textures
+    for k, (q0, u, v) in enumerate((((-3, 12, -3), (6, 0, 0), (0, 0, 6)), ((-40, -12, -40), (80, 0, 0), (0, 0, 80)))):
+        q = quads[nq + k]
+        q.Q[:], q.u[:], q.v[:] = q0, u, v
+        q.material, q.xform = d.n_materials, -1
+    world = (capi.rt_prim_ref * (d.n_world + 1))()
+    for i in range(d.n_world):
+        world[i] = d.world[i]
+    world[d.n_world].type, world[d.n_world].index = capi.RT_PRIM_QUAD, nq      # only the first of the two
+    d2 = capi.rt_scene_desc()
+    C.memmove(C.byref(d2), C.byref(d), C.sizeof(d))
+    d2.quads, d2.n_quads = quads, nq + 2
+    d2.materials, d2.n_materials = mats, d.n_materials + 1
+    d2.textures, d2.n_textures = texs, d.n_textures + 1
+    d2.world, d2.n_world = world, d.n_world + 1
+    frames = {}
+    for mode in ("host", "device"):
+        c = capi.Context(0)
+        try:
+            c.set_bvh_builder(mode)
+            c.upload(d2)
+            assert c.stats()["bvh_on_device"] == (1 if mode == "device" else 0)
+            c.render(96, 64, 8, max_depth=6, seed=4, nee=True)
+            frames[mode] = c.accum_download()
+        finally:
+            c.close()
+    assert np.array_equal(frames["host"], frames["device"])

@@ -17,7 +17,7 @@ import helpers
 
 pytestmark = pytest.mark.gpu
 
-SCENES = ["book1", "cornell", "cornell_smoke", "mesh", "final", "quads", "emissive", "specular", "mixed", "kitchen_sink"]
+SCENES = ["book1", "cornell", "cornell_smoke", "mesh", "final", "quads", "emissive", "specular", "mixed", "kitchen_sink", "monkey"]
 T_TOL = 1e-5   # relative, north_star
 N_TOL = 1e-5   # absolute on unit normals
 REPORT = {}

@@ -6,7 +6,7 @@ import pytest
 
 import helpers
 
-PRIMARY_SCENES = ["book1", "cornell", "cornell_smoke", "mesh", "final", "quads", "emissive", "specular", "mixed", "kitchen_sink"]
+PRIMARY_SCENES = ["book1", "cornell", "cornell_smoke", "mesh", "final", "quads", "emissive", "specular", "mixed", "kitchen_sink", "monkey"]
 
 
 @pytest.mark.parametrize("name", PRIMARY_SCENES)
@@ -50,7 +50,7 @@ def kat_cases(sc, g):
         yield int(m), np.nonzero(mats == m)[0]
 
 
-@pytest.mark.parametrize("name", ["kitchen_sink", "mixed", "final", "book1", "specular", "mesh"])
+@pytest.mark.parametrize("name", ["kitchen_sink", "mixed", "final", "book1", "specular", "mesh", "monkey"])
 def test_port_scatter_and_textures_equal_reference(scene_of, name):
     from oracle import port
 

@@ -10,7 +10,7 @@ import pytest
 
 import helpers
 
-SCENES = ["book1", "cornell", "cornell_smoke", "mesh", "final", "quads", "emissive", "specular", "mixed", "kitchen_sink"]
+SCENES = ["book1", "cornell", "cornell_smoke", "mesh", "final", "quads", "emissive", "specular", "mixed", "kitchen_sink", "monkey"]
 SUMMARY = json.load(open(os.path.join(helpers.GOLDEN, "scenes.json")))
 
 
