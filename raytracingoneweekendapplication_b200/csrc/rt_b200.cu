@@ -102,6 +102,9 @@ constexpr float kSampleClamp = 1048576.0f;   // 2^20: keeps 2^16 saturated sampl
 #ifndef RT_SMEM_STACK
 #define RT_SMEM_STACK 0  // binary kernel: this many traversal-stack entries per lane live in shared memory ([entry][thread]), the rest in local memory
 #endif
+#ifndef RT_STEPS_PER_VOTE
+#define RT_STEPS_PER_VOTE 1
+#endif
 #ifndef RT_V2_THREADS
 #define RT_V2_THREADS 256  // threads per block of render_kernel_v2 (tuning experiments: 224 x 3 trades warps for registers)
 #endif
@@ -250,6 +253,11 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
                                 atomicAdd(hist + 192 + min(n_leaf, 15u), 1ull);
                             }
                         }
+                        // RT_STEPS_PER_VOTE > 1: further steps of the lanes that still descend without asking the warp in between (the
+                        // vote, the reconvergence and the loop branch are 10 of a binary step's 75 instructions)
+#pragma unroll
+                        for (int extra = 1; extra < RT_STEPS_PER_VOTE; extra++)
+                            if (!STATS && tr.wants_node()) tr.template node_step<STATS>(S, ray, rc, 0.001f, stack, &st);
                     }
                 }
                 if (STATS) {
@@ -1772,6 +1780,10 @@ static int dev_render(DevCtx* ctx, const rt_render_params* p) {
     if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "rt_render: no scene uploaded");
     if (p->width <= 0 || p->height <= 0 || p->samples_per_pixel <= 0 || p->max_depth < 0 || p->spp_begin < 0)
         return fail(ctx, RT_ERR_INVALID, "rt_render: width/height/samples must be positive");
+    // a sample is clamped to 2^20 (kSampleClamp) and stored in 2^-28 units: 2^16 saturated samples fill a 64-bit sum
+    if ((long long)p->spp_begin + p->samples_per_pixel > 65536)
+        return fail(ctx, RT_ERR_UNSUPPORTED, "rt_render: samples %d + %d exceed 65536 per pixel, the capacity of the 64-bit fixed-point sums",
+                    p->spp_begin, p->samples_per_pixel);
     if ((long long)p->width * p->height >= (1ll << 31)) return fail(ctx, RT_ERR_UNSUPPORTED, "rt_render: frame too large");
     const int count = p->shard_count <= 1 ? 1 : p->shard_count;
     const int rank = count == 1 ? 0 : p->shard_rank;

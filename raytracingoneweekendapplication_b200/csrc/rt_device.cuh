@@ -370,7 +370,7 @@ struct HybridStack {
     StackEntry* local;  // entries K and up
 };
 template <int K, int STRIDE>
-__device__ __forceinline__ StackEntry stack_ld(const HybridStack<K, STRIDE>& s, int i) {
+__device__ __forceinline__ StackEntry stack_ld(HybridStack<K, STRIDE> s, int i) {
     if (i < K) {
         StackEntry v;
         asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(s.addr + (uint32_t)i * (STRIDE * 8u)));
@@ -379,7 +379,7 @@ __device__ __forceinline__ StackEntry stack_ld(const HybridStack<K, STRIDE>& s, 
     return s.local[i - K];
 }
 template <int K, int STRIDE>
-__device__ __forceinline__ void stack_st(const HybridStack<K, STRIDE>& s, int i, StackEntry v) {
+__device__ __forceinline__ void stack_st(HybridStack<K, STRIDE> s, int i, StackEntry v) {
     if (i < K) asm volatile("st.shared.u64 [%0], %1;" ::"r"(s.addr + (uint32_t)i * (STRIDE * 8u)), "l"(v) : "memory");
     else s.local[i - K] = v;
 }
@@ -403,7 +403,7 @@ struct Trav {
 
     // pop, skipping subtrees that start beyond the closest hit so far
     template <class Stack>
-    __device__ __forceinline__ void pop(const Stack& stack) {
+    __device__ __forceinline__ void pop(Stack stack) {
         cur = LINK_DONE;
         while (sp > 0) {
             sp--;
@@ -419,7 +419,7 @@ struct Trav {
     // select-based: the four outcomes (both / left / right / none) share one instruction stream,
     // the push is a predicated store, and only the (rare) "none" case branches into pop().
     template <bool STATS, class Stack>
-    __device__ __forceinline__ void interior(const DevScene& S, const RayConst& rc, float tmin, const Stack& stack, Stats* st,
+    __device__ __forceinline__ void interior(const DevScene& S, const RayConst& rc, float tmin, Stack stack, Stats* st,
                                              int* overflow) {
         const float4* n = S.nodes + 4 * (size_t)cur;
         float4 a = ldg4(n), b = ldg4(n + 1), c = ldg4(n + 2), e = ldg4(n + 3);
@@ -454,7 +454,7 @@ struct Trav {
 
     template <bool STATS, bool LITE = false, class Stack>
     __device__ __forceinline__ void leaf(const DevScene& S, const Ray& ray, const RayConst& rc, float tmin, uint32_t origin_prim,
-                                         const Stack& stack, Stats* st) {
+                                         Stack stack, Stats* st) {
         uint32_t v = ~(uint32_t)cur;
         uint32_t type = v >> 28, cnt = ((v >> 25) & 7u) + 1u, first = v & 0x1ffffffu;
         for (uint32_t i = 0; i < cnt; i++) hit_prim<STATS, LITE>(S, type, first + i, ray, rc.inv_a, tmin, origin_prim, hit, st);
@@ -462,12 +462,12 @@ struct Trav {
     }
 
     template <bool STATS, class Stack>
-    __device__ __forceinline__ void node_step(const DevScene& S, const Ray&, const RayConst& rc, float tmin, const Stack& stack, Stats* st) {
+    __device__ __forceinline__ void node_step(const DevScene& S, const Ray&, const RayConst& rc, float tmin, Stack stack, Stats* st) {
         interior<STATS>(S, rc, tmin, stack, st, nullptr);
     }
     template <bool STATS, bool LITE, class Stack>
     __device__ __forceinline__ void leaf_step(const DevScene& S, const Ray& ray, const RayConst& rc, float tmin, uint32_t origin_prim,
-                                              const Stack& stack, Stats* st) {
+                                              Stack stack, Stats* st) {
         leaf<STATS, LITE>(S, ray, rc, tmin, origin_prim, stack, st);
     }
 };
@@ -573,14 +573,17 @@ __device__ __forceinline__ int media_hit(const DevScene& S, const Ray& ray, floa
 // ---------------------------------------------------------------------------------
 // textures (texture.h) and Perlin noise (perlin.h)
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ float perlin_noise(const DevScene& S, int pidx, double px, double py, double pz) {
+// perlin.h:14-37.  FP32 throughout, and EXACT where it matters: the octave scaling p * 2^k only changes the exponent,
+// floorf of a float is a float, and px - floorf(px) needs no more bits than px has, so the lattice cell and the
+// fractional position are the same numbers a double-precision split of the same (FP32) point would give -- without the
+// FP64 conversions the first version spent on it (3.3 % of C5's time at 2.4 lanes for ONE marble sphere).
+__device__ __forceinline__ float perlin_noise(const DevScene& S, int pidx, float px, float py, float pz) {
     const float4* vec = S.perlin_vec + 256 * (size_t)pidx;
     const unsigned char* perm = S.perlin_perm + 768 * (size_t)pidx;
-    // the lattice split is done in double: 2^6 * p reaches ~1e5 in the book-2 scene, where an
-    // FP32 fractional part would have only ~8 good bits
-    double fx = floor(px), fy = floor(py), fz = floor(pz);
-    float u = (float)(px - fx), v = (float)(py - fy), w = (float)(pz - fz);
-    int i = (int)fx, j = (int)fy, k = (int)fz;
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const float u = px - fx, v = py - fy, w = pz - fz;
+    // the lattice index modulo 256 (perlin.h:25-27 `& 255`): beyond 2^31 the float is a multiple of 256 anyway
+    const int i = fabsf(fx) < 2.0e9f ? (int)fx : 0, j = fabsf(fy) < 2.0e9f ? (int)fy : 0, k = fabsf(fz) < 2.0e9f ? (int)fz : 0;
     float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
     float accum = 0.0f;
 #pragma unroll
@@ -599,11 +602,11 @@ __device__ __forceinline__ float perlin_noise(const DevScene& S, int pidx, doubl
 
 __device__ __forceinline__ float perlin_turb(const DevScene& S, int pidx, V3 p, int depth) {
     float accum = 0.0f, weight = 1.0f;
-    double x = p.x, y = p.y, z = p.z;
+    float x = p.x, y = p.y, z = p.z;
     for (int i = 0; i < depth; i++) {
         accum += weight * perlin_noise(S, pidx, x, y, z);
         weight *= 0.5f;
-        x *= 2.0; y *= 2.0; z *= 2.0;
+        x *= 2.0f; y *= 2.0f; z *= 2.0f;
     }
     return fabsf(accum);
 }

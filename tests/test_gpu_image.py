@@ -167,11 +167,20 @@ def test_both_kernel_versions_render_the_same_bits(built, scene_of):
     """render_kernel (v1, fixed ownership), render_kernel_v2 (warp streams), render_kernel_v3 (two
     path contexts per lane, rt_kernel_v3.cuh) and the wavefront pipeline (rt_wavefront.cuh)
     schedule the same samples completely differently; fixed-point sums make the frames
-    bit-identical."""
+    bit-identical.  The three alternatives lose to v2 on every BASELINE scene and are compiled only with
+    -DRT_B200_ALT_KERNELS (`python -m raytracingoneweekendapplication_b200.build --alt`): the default library refuses them."""
     import os
 
     from raytracingoneweekendapplication_b200 import capi
 
+    os.environ["RT_B200_KERNEL"] = "v1"
+    try:
+        capi.Context(0).close()
+    except capi.RtError as e:
+        assert e.code == capi.RT_ERR_UNSUPPORTED and "RT_B200_ALT_KERNELS" in str(e)
+        pytest.skip("the alternative kernels are not compiled into the default library")
+    finally:
+        os.environ.pop("RT_B200_KERNEL", None)
     frames = []
     for version in ("v1", "v2", "wf", "v3"):
         os.environ["RT_B200_KERNEL"] = version
