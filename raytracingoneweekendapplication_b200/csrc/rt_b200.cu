@@ -1864,8 +1864,10 @@ static int dev_render(DevCtx* ctx, const rt_render_params* p) {
     const unsigned long long resident_warps = (unsigned long long)grid * (ctx->kernel_version == 2 ? RT_V2_THREADS / 32 : 8);
     int n_seg = 1;
     if (A.n_local_samples > 0 && pixel_blocks > 0) {
-        // >= 64 items per resident warp: the end-of-kernel tail is one item long
-        unsigned long long want = (resident_warps * 64ull + pixel_blocks - 1) / pixel_blocks;
+        // >= kItemsPerWarp items per resident warp: the end-of-kernel tail is one item long
+        unsigned long long per_warp = 64;
+        if (const char* e = getenv("RT_B200_ITEMS_PER_WARP")) per_warp = (unsigned long long)std::max(1, atoi(e));  // tuning experiments
+        unsigned long long want = (resident_warps * per_warp + pixel_blocks - 1) / pixel_blocks;
         if (want < 1) want = 1;
         if (want > (unsigned long long)A.n_local_samples) want = A.n_local_samples;
         n_seg = (int)want;

@@ -60,7 +60,7 @@ def test_primary_hits_and_images_match_the_host_path(scene_of, name):
     assert same_px.mean() >= (0.99 if tie.any() else 1.0), f"{name}: {(~same_px).sum()} pixels differ"
 
 
-@pytest.mark.parametrize("name", ["final", "mesh", "book1", "mixed"])
+@pytest.mark.parametrize("name", ["final", "mesh", "book1", "cornell"])
 def test_device_built_tree_against_the_reference_fixture(scene_of, name):
     """The device-built tree checked DIRECTLY against the fixture dumped from the unmodified reference
     (not only against the host-built tree): the gate of test_gpu_primary.py with set_bvh_builder('device')."""
