@@ -390,6 +390,22 @@ __device__ __forceinline__ void traverse_uploaded(const DevScene& S, const Ray& 
     else traverse_sel<2>(S, ray, tmin, tmax, PRIM_NONE, hit);
 }
 
+// The builders (host SAH, device LBVH + SAH top) write a node as {lmin, llink | lmax, rlink | rmin, - | rmax, -}.  The
+// traversal reads the PAIRED form {lmin.x, rmin.x, lmin.y, rmin.y | lmin.z, rmin.z, lmax.x, rmax.x | lmax.y, rmax.y,
+// lmax.z, rmax.z | llink, rlink, -, -}: the same plane of both children in one 64-bit register pair, which is what FFMA2
+// takes (Trav::interior).  Same 64 bytes, permuted once at upload (host trees on the host, device-built trees in place).
+__host__ __device__ inline void pair_node(float4* n) {
+    const float4 a = n[0], b = n[1], c = n[2], e = n[3];
+    n[0] = make_float4(a.x, c.x, a.y, c.y);
+    n[1] = make_float4(a.z, c.z, b.x, e.x);
+    n[2] = make_float4(b.y, e.y, b.z, e.z);
+    n[3] = make_float4(a.w, b.w, 0.0f, 0.0f);
+}
+__global__ void pair_nodes_kernel(float4* __restrict__ nodes, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pair_node(nodes + 4 * (size_t)i);
+}
+
 // Camera.txt:136-168 in double: the pixel-centre ray of pixel (i, j) is center + t * (dir00 + i du + j dv)
 struct CameraD {
     double center[3], dir00[3], du[3], dv[3];
@@ -1207,6 +1223,9 @@ static int upload_scene_impl(DevCtx* ctx, const rt_scene_desc* sc, bool device_b
     std::vector<float4> nodes(bvh.nodes.size() * 4);
     static_assert(sizeof(rtbvh::Node) == 64, "node layout");
     std::memcpy(nodes.data(), bvh.nodes.data(), bvh.nodes.size() * 64);
+#if RT_NODE_PAIRED
+    for (size_t i = 0; i < bvh.nodes.size(); i++) pair_node(&nodes[4 * i]);
+#endif
 
     // ---- the wide quantised tree, collapsed from the SAH BVH2 (host-built scenes) -----------------
     rtwide::Built wide;
@@ -1340,6 +1359,13 @@ static int upload_scene_impl(DevCtx* ctx, const rt_scene_desc* sc, bool device_b
             *too_deep = true;
             return RT_OK;
         }
+#if RT_NODE_PAIRED
+        if (device_nodes > 0) {
+            pair_nodes_kernel<<<(device_nodes + 255) / 256, 256, 0, ctx->stream>>>((float4*)S.nodes, device_nodes);
+            CU(ctx, cudaGetLastError());
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+#endif
     }
     ctx->stats.bvh_on_device = device_build ? 1 : 0;
     S.root = root;
