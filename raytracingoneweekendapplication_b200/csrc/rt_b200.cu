@@ -135,6 +135,10 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
     const unsigned lt_mask = (1u << lane) - 1u;
     Stats st;
     if (STATS) memset(&st, 0, sizeof st);
+#if RT_PERLIN_SMEM
+    stage_perlin(S);
+    __syncthreads();
+#endif
 
     // warp-uniform pool of (pixel, sample) pairs
     unsigned pool_pos = 0, pool_size = 0;
@@ -740,6 +744,11 @@ static int dev_create(DevCtx** out, const int* device_ids, int n_devices) {
     cudaFuncSetAttribute(render_kernel_v2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+#if RT_PERLIN_SMEM  // measurement build: room for three blocks' tables
+    cudaFuncSetAttribute(render_kernel_v2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 10);
+    cudaFuncSetAttribute(render_kernel_v2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 10);
+    cudaFuncSetAttribute(render_kernel_v2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 10);
+#endif
     if (const char* bv = getenv("RT_B200_BVH"))
         ctx->bvh_builder = strcmp(bv, "host") == 0 ? 1 : (strcmp(bv, "device") == 0 ? 2 : (strcmp(bv, "lbvh") == 0 ? 3 : 0));
     if (const char* wv = getenv("RT_B200_BVH_WIDTH")) {

@@ -601,9 +601,30 @@ __device__ __forceinline__ int media_hit(const DevScene& S, const Ray& ray, floa
 // floorf of a float is a float, and px - floorf(px) needs no more bits than px has, so the lattice cell and the
 // fractional position are the same numbers a double-precision split of the same (FP32) point would give -- without the
 // FP64 conversions the first version spent on it (3.3 % of C5's time at 2.4 lanes for ONE marble sphere).
+#ifndef RT_PERLIN_SMEM
+#define RT_PERLIN_SMEM 0  // measurement only (north_star: "Perlin permutation tables are staged in shared memory"): the tables of
+                          // perlin 0 (4864 B per block) copied to shared memory when render_kernel_v2 starts.  Measured against
+                          // the global/L1 path in profiles/r2_perlin_smem_ab.txt; the default stays 0.
+#endif
+#if RT_PERLIN_SMEM
+__shared__ float4 sh_perlin_vec[256];
+__shared__ unsigned char sh_perlin_perm[768];
+__device__ __forceinline__ void stage_perlin(const DevScene& S) {
+    if (S.perlin_vec == nullptr) return;
+    for (unsigned i = threadIdx.x; i < 256u; i += blockDim.x) sh_perlin_vec[i] = S.perlin_vec[i];
+    for (unsigned i = threadIdx.x; i < 768u; i += blockDim.x) sh_perlin_perm[i] = S.perlin_perm[i];
+}
+#endif
 __device__ __forceinline__ float perlin_noise(const DevScene& S, int pidx, float px, float py, float pz) {
+#if RT_PERLIN_SMEM
+    const float4* vec = pidx == 0 ? sh_perlin_vec : S.perlin_vec + 256 * (size_t)pidx;
+    const unsigned char* perm = pidx == 0 ? sh_perlin_perm : S.perlin_perm + 768 * (size_t)pidx;
+#define RT_PERLIN_LD(p) (*(p))
+#else
     const float4* vec = S.perlin_vec + 256 * (size_t)pidx;
     const unsigned char* perm = S.perlin_perm + 768 * (size_t)pidx;
+#define RT_PERLIN_LD(p) __ldg(p)
+#endif
     const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
     const float u = px - fx, v = py - fy, w = pz - fz;
     // the lattice index modulo 256 (perlin.h:25-27 `& 255`): beyond 2^31 the float is a multiple of 256 anyway
@@ -616,8 +637,8 @@ __device__ __forceinline__ float perlin_noise(const DevScene& S, int pidx, float
         for (int dj = 0; dj < 2; dj++)
 #pragma unroll
             for (int dk = 0; dk < 2; dk++) {
-                int h = __ldg(perm + ((i + di) & 255)) ^ __ldg(perm + 256 + ((j + dj) & 255)) ^ __ldg(perm + 512 + ((k + dk) & 255));
-                float4 g = ldg4(vec + h);
+                int h = RT_PERLIN_LD(perm + ((i + di) & 255)) ^ RT_PERLIN_LD(perm + 256 + ((j + dj) & 255)) ^ RT_PERLIN_LD(perm + 512 + ((k + dk) & 255));
+                float4 g = RT_PERLIN_LD(vec + h);
                 float wx = u - di, wy = v - dj, wz = w - dk;
                 accum += (di ? uu : 1.0f - uu) * (dj ? vv : 1.0f - vv) * (dk ? ww : 1.0f - ww) * (g.x * wx + g.y * wy + g.z * wz);
             }
