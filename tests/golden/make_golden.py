@@ -10,7 +10,7 @@ oracle/Makefile) in this container and stores, per scene:
                         with scripted uniforms
   image_<scene>.npz     a converged float radiance image (linear, before gamma) + its spp
 
-Usage:  python tests/golden/make_golden.py [primary] [kat] [image] [image_quarter] [--scenes a,b,c]
+Usage:  python tests/golden/make_golden.py [primary] [kat] [image] [image_quarter] [--scenes=a,b,c]
 The fixtures are committed; /root/reference is not needed to run the tests.
 """
 from __future__ import annotations
