@@ -150,6 +150,26 @@ __device__ __forceinline__ V3 fma3(float s, V3 a, V3 b) { return V3{fmaf(s, a.x,
 __device__ __forceinline__ V3 normalize(V3 a) { return rsqrtf(dot(a, a)) * a; }
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+// node / primitive loads with an L1 eviction priority (tuning experiment, -DRT_NODE_HINT=1 evict_last, 2 evict_first;
+// -DRT_PRIM_HINT likewise): the working set of C5 (nodes 140 KB + primitives 420 KB + shading records) is larger than L1
+#ifndef RT_PREFETCH_FAR
+#define RT_PREFETCH_FAR 0
+#endif
+#ifndef RT_NODE_HINT
+#define RT_NODE_HINT 0
+#endif
+#ifndef RT_PRIM_HINT
+#define RT_PRIM_HINT 0
+#endif
+template <int HINT>
+__device__ __forceinline__ float4 ldg4_hint(const float4* p) {
+    if (HINT == 0) return __ldg(p);
+    float4 v;
+    if (HINT == 1) asm("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    else if (HINT == 2) asm("ld.global.nc.L1::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    else asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 
 #ifndef RT_NODE_PAIRED
 #define RT_NODE_PAIRED 1
@@ -320,13 +340,13 @@ __device__ __forceinline__ void hit_prim(const DevScene& S, uint32_t type, uint3
     uint32_t prim = (type << 28) | idx;
     if (type == PT_SPHERE) {
         if (STATS) st->sphere_tests++;
-        float4 s = ldg4(S.sph + idx);
+        float4 s = ldg4_hint<RT_PRIM_HINT>(S.sph + idx);
         hit_sphere<STATS>(v3(s), s.w, S.sph_d + 4 * (size_t)idx, false, prim == origin_prim, ray, inv_a, tmin, prim, hit, st);
     } else if (type == PT_QUAD) {
         if (STATS) st->quad_tests++;
         if (prim == origin_prim) return;  // a ray leaving a planar primitive cannot hit it again
         const float4* q = S.quad + 3 * (size_t)idx;
-        hit_quad(ldg4(q), ldg4(q + 1), ldg4(q + 2), ray, tmin, prim, hit);
+        hit_quad(ldg4_hint<RT_PRIM_HINT>(q), ldg4_hint<RT_PRIM_HINT>(q + 1), ldg4_hint<RT_PRIM_HINT>(q + 2), ray, tmin, prim, hit);
     } else if (!LITE && type == PT_TRI) {
         if (STATS) st->tri_tests++;
         if (prim == origin_prim) return;
@@ -435,7 +455,7 @@ struct Trav {
     __device__ __forceinline__ void interior(const DevScene& S, const RayConst& rc, float tmin, Stack stack, Stats* st,
                                              int* overflow) {
         const float4* n = S.nodes + 4 * (size_t)cur;
-        float4 a = ldg4(n), b = ldg4(n + 1), c = ldg4(n + 2), e = ldg4(n + 3);
+        float4 a = ldg4_hint<RT_NODE_HINT>(n), b = ldg4_hint<RT_NODE_HINT>(n + 1), c = ldg4_hint<RT_NODE_HINT>(n + 2), e = ldg4_hint<RT_NODE_HINT>(n + 3);
         if (STATS) { st->node_visits++; st->box_tests += 2; }
 #if RT_NODE_PAIRED
         // paired layout (pair_nodes): the same plane of the left and the right box sit side by side, so one
@@ -471,6 +491,14 @@ struct Trav {
             // STACK_SIZE levels or more.  The masked index + overflow flag this replaces cost 2.5 % on C5.
             stack_st(stack, sp, pack_entry(far_l, far_t));
             sp++;
+#if RT_PREFETCH_FAR == 1  // tuning experiment: the pushed subtree's root node on its way to L1 while the near one is walked
+            if (far_l >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(S.nodes + 4 * (size_t)far_l));
+#elif RT_PREFETCH_FAR == 2
+            if (far_l >= 0) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(S.nodes + 4 * (size_t)far_l));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(S.nodes + 4 * (size_t)far_l + 2));
+            }
+#endif
         }
         if (hl || hr) cur = near_l;
         else pop(stack);
