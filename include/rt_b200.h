@@ -231,6 +231,16 @@ typedef enum rt_shard_mode {
                                  term of Camera.txt:240-272.  The reference's point lights are unshadowed, so this
                                  changes the image on purpose. */
 
+#define RT_FLAG_OVERLAP 64u   /* with RT_FLAG_ASYNC | RT_FLAG_ACCUMULATE: consecutive passes onto the same frame run on two
+                                 internal streams of the context, each with its own work counter, so that the drain of one
+                                 pass (its last paths, up to max_depth dependent bounces while most SMs idle: ~1 ms on C5)
+                                 overlaps the start of the next.  The sums are order-independent integers, so the frame
+                                 is bit-identical to serial passes.  The passes are ordered after what `stream` holds when
+                                 rt_render is called; `stream` itself does NOT wait for them: call rt_join (stream order)
+                                 or anything that waits (rt_sync, rt_download, rt_resolve_tiles, ...) before using the
+                                 frame.  Ignored (a plain asynchronous pass) without both other flags and with
+                                 RT_FLAG_STATS.  rt_stats.render_ms is then the average per overlapped pass. */
+
 typedef struct rt_render_params {
     uint32_t struct_size;
     int32_t width, height;       /* image_width, image_height (Camera.txt:39,137) */
@@ -340,6 +350,11 @@ int rt_set_bvh_width(rt_ctx* ctx, int32_t width);
  * RT_FLAG_ASYNC. */
 int rt_render(rt_ctx* ctx, const rt_render_params* params);
 int rt_sync(rt_ctx* ctx);
+/* Stream-ordered join, no host wait: whatever is enqueued on `stream` (a cudaStream_t of the context's device; NULL = the
+ * context's own stream) after this call runs after every rt_render pass still in flight, RT_FLAG_OVERLAP passes included.
+ * Single-device contexts take any stream; a multi-device context joins each device's passes into that device's own
+ * stream (stream must be NULL). */
+int rt_join(rt_ctx* ctx, void* stream);
 
 /* Copy the finished frame to the host.  Either pointer may be NULL.
  *   rgb_linear: width*height*3 floats, radiance averaged over the accumulated spp,

@@ -23,6 +23,7 @@ RT_PRIM_SPHERE, RT_PRIM_QUAD, RT_PRIM_TRIANGLE = range(3)
 RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_CHECKER_TRIANGLE, RT_TEX_IMAGE, RT_TEX_NOISE = range(5)
 RT_SHARD_AUTO, RT_SHARD_TILES, RT_SHARD_SAMPLES = range(3)
 RT_FLAG_ACCUMULATE, RT_FLAG_ASYNC, RT_FLAG_STATS, RT_FLAG_NEE, RT_FLAG_SHADOWED_POINT_LIGHTS, RT_FLAG_COMPACT_TILES = 1, 2, 4, 8, 16, 32
+RT_FLAG_OVERLAP = 64
 
 d3 = C.c_double * 3
 
@@ -136,7 +137,7 @@ EXPORTED_SYMBOLS = [
     "rt_accum_buffer", "rt_bind_accum", "rt_get_stats", "rt_measure_fp32_peak", "rt_probe_texture", "rt_probe_scatter",
     "rt_probe_hit", "rt_struct_size", "rt_accum_download", "rt_accum_upload", "rt_set_bvh_builder",
     "rt_set_bvh_width", "rt_device_count", "rt_shard_pixels", "rt_resolve_tiles", "rt_untile",
-    "rt_download_begin", "rt_untile_begin", "rt_frame_end", "rt_measure_l1_peak", "rt_visible_devices",
+    "rt_download_begin", "rt_untile_begin", "rt_frame_end", "rt_measure_l1_peak", "rt_visible_devices", "rt_join",
 ]
 
 ABI_STRUCTS = [rt_scene_desc, rt_render_params, rt_stats, rt_sphere, rt_quad, rt_triangle, rt_medium, rt_material, rt_texture,
@@ -180,6 +181,7 @@ def load() -> C.CDLL:
     lib.rt_upload_scene.argtypes = [vp, C.POINTER(rt_scene_desc)]
     lib.rt_render.argtypes = [vp, C.POINTER(rt_render_params)]
     lib.rt_sync.argtypes = [vp]
+    lib.rt_join.argtypes = [vp, vp]
     lib.rt_download.argtypes = [vp, i32, vp, vp]
     lib.rt_render_aov.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     lib.rt_accum_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -346,7 +348,7 @@ class Context:
     def render(self, width: int, height: int, spp: int, max_depth: int = 50, seed: int = 1, spp_begin: int = 0,
                accumulate: bool = False, stats: bool = False, shard_rank: int = 0, shard_count: int = 1,
                shard_mode: int = RT_SHARD_AUTO, tile_size: int = 0, stream: Optional[int] = None, blocking: bool = True,
-               nee: bool = False, shadowed_point_lights: bool = False, compact: bool = False) -> None:
+               nee: bool = False, shadowed_point_lights: bool = False, compact: bool = False, overlap: bool = False) -> None:
         p = rt_render_params()
         p.struct_size = C.sizeof(rt_render_params)
         p.width, p.height, p.samples_per_pixel, p.max_depth = width, height, spp, max_depth
@@ -354,13 +356,17 @@ class Context:
         p.shard_mode, p.shard_rank, p.shard_count = shard_mode, shard_rank, shard_count
         p.flags = ((RT_FLAG_ACCUMULATE if accumulate else 0) | (RT_FLAG_STATS if stats else 0) | (0 if blocking else RT_FLAG_ASYNC) |
                    (RT_FLAG_NEE if nee else 0) | (RT_FLAG_SHADOWED_POINT_LIGHTS if shadowed_point_lights else 0) |
-                   (RT_FLAG_COMPACT_TILES if compact else 0))
+                   (RT_FLAG_COMPACT_TILES if compact else 0) | (RT_FLAG_OVERLAP if overlap else 0))
         p.stream = stream
         self._check(self.lib.rt_render(self._h, C.byref(p)))
         self.width, self.height = width, height
 
     def sync(self) -> None:
         self._check(self.lib.rt_sync(self._h))
+
+    def join(self, stream: Optional[int] = None) -> None:
+        """Stream-ordered join (no host wait): `stream` runs on after every pass still in flight (RT_FLAG_OVERLAP)."""
+        self._check(self.lib.rt_join(self._h, stream))
 
     def download(self, total_spp: int, linear: bool = True, rgb8: bool = False):
         n = self.width * self.height

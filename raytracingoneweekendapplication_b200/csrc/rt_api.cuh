@@ -258,6 +258,17 @@ extern "C" int rt_render(rt_ctx* ctx, const rt_render_params* p) {
     return RT_OK;
 }
 
+extern "C" int rt_join(rt_ctx* ctx, void* stream) {
+    RT_NEED(ctx);
+    if (ctx->dev.size() == 1) return fwd(ctx, ctx->dev[0], dev_join(ctx->dev[0], (cudaStream_t)stream));
+    if (stream) return failx(ctx, RT_ERR_INVALID, "rt_join: a multi-device context joins into its own streams (stream must be NULL)");
+    for (DevCtx* d : ctx->dev) {
+        int rc = dev_join(d, nullptr);
+        if (rc != RT_OK) return fwd(ctx, d, rc);
+    }
+    return RT_OK;
+}
+
 extern "C" int rt_sync(rt_ctx* ctx) {
     RT_NEED(ctx);
     for (DevCtx* d : ctx->dev) {

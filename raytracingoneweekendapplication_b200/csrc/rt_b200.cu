@@ -643,6 +643,13 @@ struct DevCtx {
     size_t staged_bytes = 0;
     int bvh_width = RT_B200_DEFAULT_BVH_WIDTH;
     int wide_depth = 0;  // levels of the uploaded wide tree = stack entries a ray can need
+    // RT_FLAG_OVERLAP: asynchronous accumulate passes alternate between two streams of the context, each with its own work
+    // counter (counters + 4 and + 8), so that the drain of one pass runs while the next takes over the freed SM slots
+    cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    cudaEvent_t lane_end[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ov_begin = nullptr;
+    bool lane_busy[2] = {false, false};
+    int lane_next = 0, ov_passes = 0;
     bool pending_async = false;           // an RT_FLAG_ASYNC render has not been waited for yet (dev_wait)
     bool pending_stats = false;
     cudaStream_t pending_stream = nullptr;  // the stream it was enqueued on
@@ -735,7 +742,7 @@ static int dev_create(DevCtx** out, const int* device_ids, int n_devices) {
     CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(ctx, cudaEventCreate(&ctx->ev0));
     CU(ctx, cudaEventCreate(&ctx->ev1));
-    CU(ctx, cudaMalloc(&ctx->counters, 4 * sizeof(unsigned long long)));
+    CU(ctx, cudaMalloc(&ctx->counters, 12 * sizeof(unsigned long long)));  // {work counter, guard flag, -, -} x (plain, overlap lane 0, lane 1)
     CU(ctx, cudaMalloc(&ctx->dstats, sizeof(Stats) + kTravHistBins * sizeof(unsigned long long)));
     // local-memory traversal stacks live in L1: prefer L1 over shared memory (the wide instances
     // get their carve-out per launch, from the depth of the uploaded tree)
@@ -808,6 +815,12 @@ static void dev_destroy(DevCtx* ctx) {
     if (ctx->dstats) cudaFree(ctx->dstats);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->lane_stream[k]) { cudaStreamSynchronize(ctx->lane_stream[k]); cudaStreamDestroy(ctx->lane_stream[k]); }
+        if (ctx->lane_end[k]) cudaEventDestroy(ctx->lane_end[k]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ov_begin) cudaEventDestroy(ctx->ov_begin);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
     for (auto& f : ctx->frames) {
@@ -1640,10 +1653,31 @@ static int dev_accum_upload(DevCtx* ctx, const uint64_t* host, size_t bytes, int
 
 // Finish what an RT_FLAG_ASYNC render left pending: wait for the stream it ran on, read the device time, the
 // guard counters and (STATS) the counters.  Everything that touches the frame or the scene calls this first.
+static int dev_wait_lanes(DevCtx* ctx, float* ms_per_pass) {
+    float ms_max = 0.0f;
+    bool had = false;
+    for (int k = 0; k < 2; k++) {
+        if (!ctx->lane_busy[k]) continue;
+        ctx->lane_busy[k] = false;
+        had = true;
+        CU(ctx, cudaEventSynchronize(ctx->lane_end[k]));
+        float ms = 0.0f;
+        CU(ctx, cudaEventElapsedTime(&ms, ctx->ov_begin, ctx->lane_end[k]));
+        ms_max = std::max(ms_max, ms);
+    }
+    *ms_per_pass = had && ctx->ov_passes > 0 ? ms_max / (float)ctx->ov_passes : -1.0f;
+    ctx->ov_passes = 0;
+    return RT_OK;
+}
+
 static int dev_wait(DevCtx* ctx) {
     CU(ctx, cudaSetDevice(ctx->device));
+    float ov_ms = -1.0f;
+    int rcl = dev_wait_lanes(ctx, &ov_ms);  // overlapped passes (RT_FLAG_OVERLAP) first: they follow the pending plain pass
+    if (rcl != RT_OK) return rcl;
     if (!ctx->pending_async) {
         CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ov_ms >= 0.0f) ctx->stats.render_ms = ov_ms;
         return RT_OK;
     }
     ctx->pending_async = false;
@@ -1657,6 +1691,7 @@ static int dev_wait(DevCtx* ctx) {
     CU(ctx, cudaMemcpyAsync(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (c[1]) return fail(ctx, RT_ERR_KERNEL, "traversal stack overflow (BVH deeper than %d)", STACK_SIZE);
+    if (ov_ms >= 0.0f) ctx->stats.render_ms = ov_ms;
     if (ctx->pending_stats) {
         Stats h;
         CU(ctx, cudaMemcpyAsync(&h, ctx->dstats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1681,6 +1716,18 @@ static int dev_wait(DevCtx* ctx) {
         ctx->stats.shade_iters = h.shade_iters;
         ctx->stats.shade_lanes = h.shade_lanes;
     }
+    return RT_OK;
+}
+
+// Orders `stream` (NULL: the context's own) after every render the context still has in flight -- the pending
+// asynchronous pass and the RT_FLAG_OVERLAP passes on the lane streams.  No host wait.
+static int dev_join(DevCtx* ctx, cudaStream_t stream) {
+    if (!ctx) return RT_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!stream) stream = ctx->stream;
+    for (int k = 0; k < 2; k++)
+        if (ctx->lane_busy[k]) CU(ctx, cudaStreamWaitEvent(stream, ctx->lane_end[k], 0));
+    if (ctx->pending_async && ctx->pending_stream != stream) CU(ctx, cudaStreamWaitEvent(stream, ctx->ev1, 0));
     return RT_OK;
 }
 
@@ -1794,7 +1841,8 @@ static int v2_blocks_per_sm(DevCtx* ctx, int variant, int width, int* out) {
     return RT_OK;
 }
 
-static int launch_v2(DevCtx* ctx, int variant, int width, int grid, const RenderArgs& A, cudaStream_t stream) {
+static int launch_v2(DevCtx* ctx, int variant, int width, int grid, const RenderArgs& A, cudaStream_t stream, unsigned long long* counters = nullptr) {
+    if (!counters) counters = ctx->counters;
     width = v2_effective_width(variant, width);
     size_t smem = v2_smem(ctx, width);
     // RT_B200_DUMMY_SMEM: unused dynamic shared memory per block, to measure what giving up
@@ -1805,7 +1853,7 @@ static int launch_v2(DevCtx* ctx, int variant, int width, int grid, const Render
             const int pct = (int)std::min<size_t>(100, (100 * 3 * (smem + 1024) + 233471) / 233472);
             cudaFuncSetAttribute((const void*)v2_kernel(variant, 2), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         }
-    v2_kernel(variant, width)<<<grid, RT_V2_THREADS, smem, stream>>>(ctx->scene, A, ctx->accum, ctx->counters, ctx->dstats);
+    v2_kernel(variant, width)<<<grid, RT_V2_THREADS, smem, stream>>>(ctx->scene, A, ctx->accum, counters, ctx->dstats);
     return RT_OK;
 }
 
@@ -1825,11 +1873,18 @@ static int dev_render(DevCtx* ctx, const rt_render_params* p) {
     if (rank < 0 || rank >= count) return fail(ctx, RT_ERR_INVALID, "rt_render: shard_rank %d outside [0,%d)", rank, count);
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t stream = p->stream ? (cudaStream_t)p->stream : ctx->stream;
+    // RT_FLAG_OVERLAP: this pass goes to one of the two lane streams with its own work counter and waits for nothing on
+    // the host; it needs the frame the passes before it render into, unchanged
+    const bool overlap = (p->flags & RT_FLAG_OVERLAP) && (p->flags & RT_FLAG_ASYNC) && (p->flags & RT_FLAG_ACCUMULATE) &&
+                         !(p->flags & RT_FLAG_STATS) && ctx->kernel_version == 2 && ctx->accum != nullptr;
     // a pending asynchronous render (possibly on another stream) shares the work counter, the guard flags and the
     // stats block with this one: finish it first
-    int rc = dev_wait(ctx);
+    int rc = overlap ? RT_OK : dev_wait(ctx);
     if (rc != RT_OK) return rc;
-    if (ctx->cam_w != p->width || ctx->cam_h != p->height) setup_camera(ctx, p->width, p->height);
+    if (ctx->cam_w != p->width || ctx->cam_h != p->height) {
+        if (overlap) return fail(ctx, RT_ERR_STATE, "rt_render: RT_FLAG_OVERLAP onto a frame of another size");
+        setup_camera(ctx, p->width, p->height);
+    }
 
     RenderArgs A;
     std::memset(&A, 0, sizeof A);
@@ -1913,6 +1968,42 @@ static int dev_render(DevCtx* ctx, const rt_render_params* p) {
     A.k0 = (uint32_t)(p->seed & 0xffffffffu);
     A.k1 = (uint32_t)(p->seed >> 32);
 
+    if (overlap) {
+        const int k = ctx->lane_next;
+        ctx->lane_next ^= 1;
+        if (!ctx->lane_stream[k]) {
+            CU(ctx, cudaStreamCreateWithFlags(&ctx->lane_stream[k], cudaStreamNonBlocking));
+            CU(ctx, cudaEventCreateWithFlags(&ctx->lane_end[k], cudaEventDefault));
+        }
+        if (!ctx->ev_fork) {
+            CU(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            CU(ctx, cudaEventCreate(&ctx->ov_begin));
+        }
+        cudaStream_t ls = ctx->lane_stream[k];
+        unsigned long long* cnt = ctx->counters + 4 * (1 + k);
+        // after everything `stream` holds now (the clearing pass, a restored checkpoint, ...); the previous pass of this
+        // lane precedes this one in stream order, the pass on the other lane runs beside it
+        CU(ctx, cudaEventRecord(ctx->ev_fork, stream));
+        CU(ctx, cudaStreamWaitEvent(ls, ctx->ev_fork, 0));
+        if (!ctx->lane_busy[0] && !ctx->lane_busy[1]) {
+            CU(ctx, cudaEventRecord(ctx->ov_begin, ls));
+            ctx->ov_passes = 0;
+        }
+        CU(ctx, cudaMemsetAsync(cnt, 0, 4 * sizeof(unsigned long long), ls));
+        if (A.n_items > 0) {
+            A.nee_emitters = want_nee;
+            A.shadow_point_lights = want_shadow;
+            rc = launch_v2(ctx, variant, width, grid, A, ls, cnt);
+            if (rc != RT_OK) return rc;
+            CU(ctx, cudaGetLastError());
+        }
+        CU(ctx, cudaEventRecord(ctx->lane_end[k], ls));
+        ctx->lane_busy[k] = true;
+        ctx->ov_passes++;
+        ctx->stats.kernel_launches = A.n_items > 0 ? 1 : 0;
+        ctx->stats.blocks = grid;
+        return RT_OK;
+    }
     if (!(p->flags & RT_FLAG_ACCUMULATE)) CU(ctx, cudaMemsetAsync(ctx->accum, 0, L.slots() * 32, stream));
     CU(ctx, cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), stream));
     if (stats) CU(ctx, cudaMemsetAsync(ctx->dstats, 0, sizeof(Stats) + kTravHistBins * sizeof(unsigned long long), stream));
@@ -2074,7 +2165,8 @@ static int dev_download_begin(DevCtx* ctx, int32_t total_spp, int32_t want_linea
     if (rc == RT_OK) rc = ensure_out(ctx, px);
     if (rc != RT_OK) return rc;
     // stream order, no host wait: the pending render (on its own stream), then the previous copy, then the resolve
-    if (ctx->pending_async && ctx->pending_stream != ctx->stream) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev1, 0));
+    rc = dev_join(ctx, ctx->stream);
+    if (rc != RT_OK) return rc;
     rc = frame_wait_prev_copy(ctx);
     if (rc == RT_OK) rc = dev_resolve_into(ctx, total_spp, want_linear ? ctx->out_lin : nullptr, want_rgb8 ? ctx->out_rgb8 : nullptr);
     if (rc != RT_OK) return rc;
