@@ -94,7 +94,8 @@ constexpr float kSampleClamp = 1048576.0f;   // 2^20: keeps 2^16 saturated sampl
 #define RT_B200_DEFAULT_BVH_WIDTH 2  // the default is decided by measurement
 #endif
 #ifndef RT_MIN_BLOCKS
-#define RT_MIN_BLOCKS 3
+#define RT_MIN_BLOCKS 4  // blocks of RT_V2_THREADS per SM the binary instances are compiled for: 4 x 256 = 32 warps at 64 registers
+                         // (round 1 ran 3 x 256 at 80 registers; re-measured on the round-2 kernel, profiles/r2_block_shape_sweep.txt)
 #endif
 #ifndef RT_WIDE_MIN_BLOCKS
 #define RT_WIDE_MIN_BLOCKS RT_MIN_BLOCKS  // blocks per SM the wide instances are compiled for (register budget)
