@@ -1524,6 +1524,9 @@ static int ensure_accum(DevCtx* ctx, const AccumLayout& L) {
 static int dev_bind_accum(DevCtx* ctx, void* device_ptr, size_t bytes, int32_t width, int32_t height) {
     if (!ctx) return RT_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
+    // passes still in flight (asynchronous, overlapped) write into the buffer that is about to be replaced
+    int rc = dev_wait(ctx);
+    if (rc != RT_OK) return rc;
     if (ctx->accum && !ctx->accum_external) cudaFree(ctx->accum);
     ctx->accum = nullptr;
     ctx->accum_external = false;
