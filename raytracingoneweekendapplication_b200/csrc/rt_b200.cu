@@ -1895,16 +1895,15 @@ static int dev_render(DevCtx* ctx, const rt_render_params* p) {
     cudaStream_t stream = p->stream ? (cudaStream_t)p->stream : ctx->stream;
     // RT_FLAG_OVERLAP: this pass goes to one of the two lane streams with its own work counter and waits for nothing on
     // the host; it needs the frame the passes before it render into, unchanged
+    // (the camera of this frame size must be set up already: the first pass onto a restored checkpoint is a plain one)
     const bool overlap = (p->flags & RT_FLAG_OVERLAP) && (p->flags & RT_FLAG_ASYNC) && (p->flags & RT_FLAG_ACCUMULATE) &&
-                         !(p->flags & RT_FLAG_STATS) && ctx->kernel_version == 2 && ctx->accum != nullptr;
+                         !(p->flags & RT_FLAG_STATS) && ctx->kernel_version == 2 && ctx->accum != nullptr &&
+                         ctx->cam_w == p->width && ctx->cam_h == p->height;
     // a pending asynchronous render (possibly on another stream) shares the work counter, the guard flags and the
     // stats block with this one: finish it first
     int rc = overlap ? RT_OK : dev_wait(ctx);
     if (rc != RT_OK) return rc;
-    if (ctx->cam_w != p->width || ctx->cam_h != p->height) {
-        if (overlap) return fail(ctx, RT_ERR_STATE, "rt_render: RT_FLAG_OVERLAP onto a frame of another size");
-        setup_camera(ctx, p->width, p->height);
-    }
+    if (ctx->cam_w != p->width || ctx->cam_h != p->height) setup_camera(ctx, p->width, p->height);
 
     RenderArgs A;
     std::memset(&A, 0, sizeof A);

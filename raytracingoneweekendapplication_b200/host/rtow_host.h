@@ -1640,16 +1640,21 @@ class camera {
         // progressive passes so the reference's progress line (Camera.txt:102-106) still ticks
         const int target = stop_after_spp > 0 ? std::min(stop_after_spp, samples_per_pixel) : samples_per_pixel;
         const int pass_spp = std::max(1, std::min(samples_per_pixel, 64));
-        int since_save = 0;
+        int since_save = 0, passes = 0;
         bool fresh = done == 0;
         while (done < target) {
             int n = std::min(pass_spp, target - done);
             if (!checkpoint_path.empty() && checkpoint_every_spp > 0) n = std::min(n, std::max(1, checkpoint_every_spp - since_save));
             p.samples_per_pixel = n;
             p.spp_begin = done;
-            p.flags = (fresh ? 0 : RT_FLAG_ACCUMULATE) | estimator_flags;
+            // passes after the first are enqueued without waiting and overlap their drains (RT_FLAG_OVERLAP: the last,
+            // longest paths of one pass run while the next fills the freed SMs; integer sums, same frame).  Every eighth
+            // pass is waited for, so that the progress line below stays within eight passes of the truth; checkpoints
+            // and the download wait for everything by themselves.
+            p.flags = (fresh ? 0 : (RT_FLAG_ACCUMULATE | RT_FLAG_ASYNC | RT_FLAG_OVERLAP)) | estimator_flags;
             fresh = false;
             if (rt_render(ctx, &p) != RT_OK) fail("rt_render");
+            if (++passes % 8 == 0 && rt_sync(ctx) != RT_OK) fail("rt_sync");
             done += n;
             since_save += n;
             if (!checkpoint_path.empty() && checkpoint_every_spp > 0 && since_save >= checkpoint_every_spp && done < samples_per_pixel) {
