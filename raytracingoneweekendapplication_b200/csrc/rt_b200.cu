@@ -131,6 +131,9 @@ struct TravSel<2> { using Trav = rtdev::Trav; using RayConst = rtdev::RayConst; 
 // One 64-bit RED into the frame.  RT_FRAME_HINT 1: with an L2 evict_first policy -- the frame (265 MB at 4K) streams through
 // the 126 MB L2 once per pass and would otherwise push out the lines that are re-used: the local-memory stacks and spills
 // (119 MB allocated at 32 warps per SM) and the scene.
+#ifndef RT_PARK_STATE
+#define RT_PARK_STATE 0
+#endif
 #ifndef RT_FRAME_HINT
 #define RT_FRAME_HINT 0  // measured: -0.5 % on C5, -3 % on C3 (profiles/r2_frame_hint_ab.txt); stays off
 #endif
@@ -164,6 +167,12 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
     // when the sample starts and read when it ends -- no register is held across the whole path for it
     __shared__ uint32_t lane_slot[RT_V2_THREADS];
     unsigned slot_base = 0;
+#if RT_PARK_STATE
+    // tuning experiment: the path state only the shade phase uses (radiance, throughput, pixel, sample, bounce) lives in
+    // shared memory [word][thread] between shade phases, so that it holds no registers (and causes no spills) across
+    // the traversal loops
+    __shared__ uint32_t park[9][RT_V2_THREADS];
+#endif
     bool exhausted = A.max_depth <= 0;  // ray_color(depth <= 0) is black before anything is traced
 
     int state = LANE_IDLE;
@@ -230,6 +239,13 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
                     L = v3(0, 0, 0);
                     T = v3(1, 1, 1);
                     bounce = 0;
+#if RT_PARK_STATE
+                    park[0][threadIdx.x] = park[1][threadIdx.x] = park[2][threadIdx.x] = 0u;
+                    park[3][threadIdx.x] = park[4][threadIdx.x] = park[5][threadIdx.x] = 0x3F800000u;
+                    park[6][threadIdx.x] = rng.pixel;
+                    park[7][threadIdx.x] = rng.sample;
+                    park[8][threadIdx.x] = 0u;
+#endif
                     origin_prim = PRIM_NONE;
                     nee_pdf = 0.0f;
                     tr.init(S, kInf);
@@ -311,6 +327,13 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
             if (lane == 0) { st.shade_iters++; st.shade_lanes += __popc(smask); }
         }
         if (state == LANE_SHADE) {
+#if RT_PARK_STATE
+            L = v3(__uint_as_float(park[0][threadIdx.x]), __uint_as_float(park[1][threadIdx.x]), __uint_as_float(park[2][threadIdx.x]));
+            T = v3(__uint_as_float(park[3][threadIdx.x]), __uint_as_float(park[4][threadIdx.x]), __uint_as_float(park[5][threadIdx.x]));
+            rng.pixel = park[6][threadIdx.x];
+            rng.sample = park[7][threadIdx.x];
+            bounce = park[8][threadIdx.x];
+#endif
             Hit hit = tr.hit;
             int medium = -1;
             if (S.n_media > 0) medium = media_hit<STATS>(S, ray, 0.001f, hit.t, rng, bounce, &st);
@@ -383,6 +406,11 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
                 }
                 state = LANE_IDLE;
             } else {
+#if RT_PARK_STATE
+                park[0][threadIdx.x] = __float_as_uint(L.x); park[1][threadIdx.x] = __float_as_uint(L.y); park[2][threadIdx.x] = __float_as_uint(L.z);
+                park[3][threadIdx.x] = __float_as_uint(T.x); park[4][threadIdx.x] = __float_as_uint(T.y); park[5][threadIdx.x] = __float_as_uint(T.z);
+                park[8][threadIdx.x] = bounce;
+#endif
                 tr.init(S, kInf);
                 state = tr.done() ? LANE_SHADE : LANE_TRAVERSE;
                 if (STATS) { st.rays++; seg_steps = n_leaf = 0; }
@@ -768,6 +796,16 @@ static int dev_create(DevCtx** out, const int* device_ids, int n_devices) {
     cudaFuncSetAttribute(render_kernel_v2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+#if RT_PARK_STATE  // measurement build: 9 words per thread of parked path state, RT_MIN_BLOCKS blocks per SM
+    {
+        const int pct = (int)((100 * RT_MIN_BLOCKS * (10 * RT_V2_THREADS * 4 + 2048) + 233471) / 233472);
+        cudaFuncSetAttribute(render_kernel_v2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(render_kernel_v2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(render_kernel_v2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(render_kernel_v2<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(render_kernel_v2<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
+#endif
 #if RT_PERLIN_SMEM  // measurement build: room for three blocks' tables
     cudaFuncSetAttribute(render_kernel_v2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 10);
     cudaFuncSetAttribute(render_kernel_v2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 10);
