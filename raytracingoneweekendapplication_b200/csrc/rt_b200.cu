@@ -1097,6 +1097,61 @@ static void setup_camera(DevCtx* ctx, int width, int height) {
 
 // `too_deep` is set when the device-built tree is deeper than the traversal stack allows; the
 // caller then repeats the upload on the host path.
+// Are these six baked primitives the faces of ONE parallelepiped (box() of quad.h:76-97 under any rigid transform)?
+// Then the boundary is the intersection of three slabs {axis_k, lo_k, hi_k} (boundary_pair_box, rt_device.cuh).
+// Checked, not assumed: three pairs of parallel quads, independent axes, and every corner of every quad on a boundary
+// plane of each of the other two slabs, with both planes of each reached (the quad IS the whole face).
+static bool box_slabs(const rtprep::BakedPrim* q, float4 out[4]) {
+    using rtprep::D3;
+    D3 n[6];
+    double dq[6], scale = 0.0;
+    for (int i = 0; i < 6; i++) {
+        if (q[i].dev_type != PT_QUAD) return false;
+        const D3 c = rtprep::dcross(q[i].b, q[i].c);
+        const double len = std::sqrt(rtprep::ddot(c, c));
+        if (!(len > 0.0)) return false;
+        n[i] = (1.0 / len) * c;
+        dq[i] = rtprep::ddot(n[i], q[i].a);
+        scale = std::max({scale, std::fabs(dq[i]), std::sqrt(rtprep::ddot(q[i].b, q[i].b)), std::sqrt(rtprep::ddot(q[i].c, q[i].c))});
+    }
+    const double tol = 1e-9 * std::max(scale, 1.0);
+    int mate[6] = {-1, -1, -1, -1, -1, -1}, axis_of[6], n_axes = 0;
+    D3 axis[3];
+    double lo[3], hi[3];
+    for (int i = 0; i < 6; i++) {
+        if (mate[i] >= 0) continue;
+        for (int j = i + 1; j < 6; j++)
+            if (mate[j] < 0 && std::fabs(std::fabs(rtprep::ddot(n[i], n[j])) - 1.0) < 1e-12) { mate[i] = j; mate[j] = i; break; }
+        if (mate[i] < 0 || n_axes == 3) return false;
+        const int j = mate[i];
+        const double dj = rtprep::ddot(n[i], q[j].a);  // the mate's plane along THIS normal
+        axis[n_axes] = n[i];
+        lo[n_axes] = std::min(dq[i], dj);
+        hi[n_axes] = std::max(dq[i], dj);
+        if (!(hi[n_axes] - lo[n_axes] > tol)) return false;
+        axis_of[i] = axis_of[j] = n_axes++;
+    }
+    if (n_axes != 3) return false;
+    if (!(std::fabs(rtprep::ddot(axis[0], rtprep::dcross(axis[1], axis[2]))) > 1e-6)) return false;
+    for (int i = 0; i < 6; i++) {
+        const D3 corner[4] = {q[i].a, q[i].a + q[i].b, q[i].a + q[i].c, q[i].a + q[i].b + q[i].c};
+        for (int k = 0; k < 3; k++) {
+            bool at_lo = false, at_hi = false;
+            for (const D3& p : corner) {
+                const double v = rtprep::ddot(axis[k], p);
+                const bool l = std::fabs(v - lo[k]) <= tol, h = std::fabs(v - hi[k]) <= tol;
+                if (!l && !h) return false;
+                at_lo |= l;
+                at_hi |= h;
+            }
+            if (k == axis_of[i] ? (at_lo && at_hi) : !(at_lo && at_hi)) return false;  // own axis: one plane; others: both
+        }
+    }
+    for (int k = 0; k < 3; k++) out[k] = make_float4((float)axis[k].x, (float)axis[k].y, (float)axis[k].z, (float)lo[k]);
+    out[3] = make_float4((float)hi[0], (float)hi[1], (float)hi[2], 0.0f);
+    return true;
+}
+
 static int upload_scene_impl(DevCtx* ctx, const rt_scene_desc* sc, bool device_build, bool* too_deep) {
     auto t_begin = std::chrono::steady_clock::now();
     const rtprep::Sources src{sc->spheres, sc->quads, sc->triangles, sc->xforms};
@@ -1272,6 +1327,7 @@ static int upload_scene_impl(DevCtx* ctx, const rt_scene_desc* sc, bool device_b
         }
     }
     std::vector<DevMedium> media((size_t)sc->n_media);
+    std::vector<float4> media_box;
     for (int i = 0; i < sc->n_media; i++) {
         const rt_medium& m = sc->media[i];
         DevMedium& d = media[i];
@@ -1283,8 +1339,14 @@ static int upload_scene_impl(DevCtx* ctx, const rt_scene_desc* sc, bool device_b
         D3 n = xf_dir(m.xform >= 0 ? &sc->xforms[m.xform] : nullptr, D3{1, 0, 0});
         d.normal[0] = (float)n.x; d.normal[1] = (float)n.y; d.normal[2] = (float)n.z;
         d.sphere = -1;
+        d.box = -1;
         if (m.boundary_count == 1 && (boundary_packed[m.boundary_first] >> 28) == PT_SPHERE)
             d.sphere = (int)(boundary_packed[m.boundary_first] & 0x0fffffffu);
+        float4 slabs[4];
+        if (m.boundary_count == 6 && !getenv("RT_B200_NO_BOX_MEDIA") && box_slabs(&baked[first_boundary + (size_t)m.boundary_first], slabs)) {
+            d.box = (int)(media_box.size() / 4);
+            media_box.insert(media_box.end(), slabs, slabs + 4);
+        }
     }
     std::vector<DevLight> lights((size_t)sc->n_lights);
     for (int i = 0; i < sc->n_lights; i++) {
@@ -1357,7 +1419,7 @@ static int upload_scene_impl(DevCtx* ctx, const rt_scene_desc* sc, bool device_b
     UPW(sph, sph, PT_SPHERE, 16) UPW(msph, msph, PT_MSPHERE, 32) UPW(quad, quad, PT_QUAD, 48) UPW(tri, tri, PT_TRI, 48)
     UPW(sph_d, sph_d, PT_SPHERE, 32) UPW(msph_d, msph_d, PT_MSPHERE, 64) UPW(quad_d, quad_d, PT_QUAD, 96) UPW(tri_d, tri_d, PT_TRI, 72)
     UPW(sph_sh, sph_sh, PT_SPHERE, 16) UPW(msph_sh, msph_sh, PT_MSPHERE, 16) UPW(quad_sh, quad_sh, PT_QUAD, 16) UPW(tri_sh, tri_sh, PT_TRI, 48)
-    UP(xrot, xrot) UP(media, media)
+    UP(xrot, xrot) UP(media, media) UP(media_box, media_box)
     UP(boundary_packed, boundary) UP(mats, mats) UP(texs, texs) UP(images, images) UP(perlin_vec, perlin_vec)
     UP(perlin_perm, perlin_perm) UP(lights, lights) UP(nee_lights, nee_lights)
 #undef UP

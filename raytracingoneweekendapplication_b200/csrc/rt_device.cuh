@@ -54,8 +54,8 @@ struct DevMedium {  // 48 B
     int material;
     float normal[3];  // R * (1,0,0)
     int sphere;  // >= 0: the boundary is this one static sphere (index into sph); -1: generic
-    float bmin[3];
-    float bmax_pad;
+    int box;     // >= 0: the boundary is the six quads of one box() (any rigid transform): three slabs, media_box + 4 * box
+    int pad[3];
 };
 // A quad emitter the opt-in next-event estimation samples: world-space
 // corner and edges, area, emission texture, and the running share of the total emitter area.
@@ -101,6 +101,7 @@ struct DevScene {
     const float4* tri_sh;  // 3 per triangle: {n.xyz, as_float(material)} {uv0, uv1} {uv2, as_float(id), 0}
     const float* xrot;     // 9 per xform: world-from-object rotation, row-major
     const DevMedium* media;
+    const float4* media_box;  // per box-bounded medium: {axis0, lo0} {axis1, lo1} {axis2, lo2} {hi0, hi1, hi2, -}
     int n_media;
     const uint32_t* boundary;  // packed prim refs type<<28 | index
     const DevMaterial* mats;
@@ -565,6 +566,31 @@ __device__ __noinline__ bool boundary_pair_generic(const DevScene& S, int bfirst
     return true;
 }
 
+// The same two calls against a boundary that is ONE box() (box() in quad.h: six quads, the faces of a parallelepiped;
+// both smoke volumes of the Cornell scene): the line enters the closed box at the nearest of the (at most two) faces it
+// crosses -- what hit(universe) over the six quads returns -- and leaves it at the other one -- what hit(t1 + 1e-4, inf)
+// returns; both come out of ONE three-slab test instead of twelve quad tests.  A line that misses the box, or only
+// touches it (exit within 1e-4 of the entry), is no boundary pair, as there.  quad.h:35's parallel-plane rejection
+// (|n.d| < 1e-8) becomes the slab's inside/outside test for that axis.
+__device__ __noinline__ bool boundary_pair_box(const float4* __restrict__ bx, const Ray& ray, float& t1, float& t2) {
+    const float4 a0 = ldg4(bx), a1 = ldg4(bx + 1), a2 = ldg4(bx + 2), hi = ldg4(bx + 3);
+    float t_in = -__int_as_float(0x7f800000), t_out = __int_as_float(0x7f800000);
+    auto slab = [&](float4 a, float h) -> bool {
+        const float dn = dot(v3(a), ray.d), on = dot(v3(a), ray.o);
+        if (fabsf(dn) < 1e-8f) return on >= a.w && on <= h;
+        const float inv = __fdividef(1.0f, dn);
+        const float ta = (a.w - on) * inv, tb = (h - on) * inv;
+        t_in = fmaxf(t_in, fminf(ta, tb));
+        t_out = fminf(t_out, fmaxf(ta, tb));
+        return true;
+    };
+    if (!slab(a0, hi.x) || !slab(a1, hi.y) || !slab(a2, hi.z)) return false;
+    if (!(t_in <= t_out)) return false;
+    t1 = t_in;
+    t2 = t_out;
+    return t_out > t_in + 0.0001f;
+}
+
 // constant_medium.h:20-53 for every medium, against the closest surface hit so far.
 // Returns the index of the medium that scattered the ray (or -1) and updates t_hit.
 // A boundary that is one static sphere (both media of the book-2 scene) takes ONE quadratic:
@@ -587,7 +613,7 @@ __device__ __forceinline__ int media_hit(const DevScene& S, const Ray& ray, floa
         if ((m & 3) == 0) u4 = rng.draw(bounce, RS_MEDIUM + (m >> 2));
         float u = (m & 3) == 0 ? u4.x : ((m & 3) == 1 ? u4.y : ((m & 3) == 2 ? u4.z : u4.w));
         const DevMedium& md = S.media[m];
-        if (STATS) { st->medium_queries++; st->boundary_tests += 2 * md.bcount; }
+        if (STATS) { st->medium_queries++; st->boundary_tests += md.box >= 0 ? 1 : 2 * md.bcount; }  // a box boundary is one three-slab test
         float t1, t2;
         if (md.sphere >= 0) {
             float4 s = ldg4(S.sph + md.sphere);
@@ -606,6 +632,8 @@ __device__ __forceinline__ int media_hit(const DevScene& S, const Ray& ray, floa
                 t2 = k + sq;
             }
             if (!(t2 > t1 + 0.0001f)) continue;
+        } else if (md.box >= 0) {
+            if (!boundary_pair_box(S.media_box + 4 * (size_t)md.box, ray, t1, t2)) continue;
         } else {
             if (!boundary_pair_generic(S, md.bfirst, md.bcount, ray, inv_a, t1, t2)) continue;
         }
@@ -1097,6 +1125,8 @@ __device__ __forceinline__ float media_transmittance(const DevScene& S, const Ra
                 t2 = k + sq;
             }
             if (!(t2 > t1 + 0.0001f)) continue;
+        } else if (md.box >= 0) {
+            if (!boundary_pair_box(S.media_box + 4 * (size_t)md.box, ray, t1, t2)) continue;
         } else {
             if (!boundary_pair_generic(S, md.bfirst, md.bcount, ray, inv_a, t1, t2)) continue;
         }

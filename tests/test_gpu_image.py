@@ -7,6 +7,7 @@ import pytest
 import torch
 
 import helpers
+from raytracingoneweekendapplication_b200 import capi
 
 pytestmark = pytest.mark.gpu
 
@@ -226,3 +227,33 @@ def test_lite_kernel_instance_renders_the_same_bits(ctx, scene_of):
     finally:
         os.environ.pop("RT_B200_NO_LITE", None)
     assert np.array_equal(lite, accum_of(ctx))
+
+
+def test_box_bounded_media_take_the_slab_test(built, scene_of, monkeypatch):
+    """A constant_medium whose boundary is one box() (both smoke volumes of C3) is intersected with ONE three-slab test
+    instead of 2 x 6 quad tests (boundary_pair_box).  Same entry/exit distances up to FP32 rounding: the counted
+    boundary tests drop to one per query, the image statistics stay, and RT_B200_NO_BOX_MEDIA=1 restores the quad path."""
+    sc = scene_of("cornell_smoke")
+    w, h, spp = 200, 200, 64
+    out = {}
+    for mode in ("slabs", "quads"):
+        if mode == "quads":
+            monkeypatch.setenv("RT_B200_NO_BOX_MEDIA", "1")
+        else:
+            monkeypatch.delenv("RT_B200_NO_BOX_MEDIA", raising=False)
+        c = capi.Context(0)
+        try:
+            c.upload(sc)
+            c.render(w, h, spp, max_depth=sc.depth, seed=3, stats=True)
+            st = c.stats()
+            out[mode] = (c.download(spp).astype(np.float64), st["medium_queries"], st["boundary_tests"])
+        finally:
+            c.close()
+    (a, qa, ba), (b, qb, bb) = out["slabs"], out["quads"]
+    assert qa > 0 and ba == qa           # one slab test per (ray, medium)
+    assert bb == 12 * qb                 # two passes over six quads
+    assert abs(qa - qb) <= 0.001 * qb    # the same rays ask
+    # the same estimator: almost every sample takes the same decisions (entry/exit distances differ in the last bits)
+    same = np.isclose(a, b, rtol=1e-4, atol=1e-6).all(axis=2).mean()
+    assert same >= 0.98, same
+    assert np.allclose(a.mean(axis=(0, 1)), b.mean(axis=(0, 1)), rtol=2e-3)
