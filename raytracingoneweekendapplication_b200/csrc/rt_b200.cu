@@ -2087,6 +2087,17 @@ static int dev_render(DevCtx* ctx, const rt_render_params* p) {
     A.k0 = (uint32_t)(p->seed & 0xffffffffu);
     A.k1 = (uint32_t)(p->seed >> 32);
 
+    // samples this pass traces: the whole frame, or the pixels of the tiles this shard owns
+    auto pass_samples = [&]() -> uint64_t {
+        if (!(mode == RT_SHARD_TILES && count > 1)) return (uint64_t)A.n_local_samples * (uint64_t)p->width * p->height;
+        uint64_t px = 0;
+        for (int t = rank; t < n_tiles; t += count) {
+            int tx = t % A.tiles_x, ty = t / A.tiles_x;
+            int w = std::min(A.tile_size, p->width - tx * A.tile_size), h = std::min(A.tile_size, p->height - ty * A.tile_size);
+            px += (uint64_t)w * h;
+        }
+        return px * (uint64_t)A.n_local_samples;
+    };
     if (overlap) {
         const int k = ctx->lane_next;
         ctx->lane_next ^= 1;
@@ -2121,6 +2132,7 @@ static int dev_render(DevCtx* ctx, const rt_render_params* p) {
         ctx->ov_passes++;
         ctx->stats.kernel_launches = A.n_items > 0 ? 1 : 0;
         ctx->stats.blocks = grid;
+        ctx->stats.samples = pass_samples();
         return RT_OK;
     }
     if (!(p->flags & RT_FLAG_ACCUMULATE)) CU(ctx, cudaMemsetAsync(ctx->accum, 0, L.slots() * 32, stream));
@@ -2154,17 +2166,7 @@ static int dev_render(DevCtx* ctx, const rt_render_params* p) {
         if (ctx->kernel_version != 3) ctx->stats.kernel_launches = 1;
     }
     ctx->stats.blocks = grid;
-    ctx->stats.samples = (uint64_t)A.n_local_samples * ((mode == RT_SHARD_TILES && count > 1) ? 0 : (uint64_t)p->width * p->height);
-    if (mode == RT_SHARD_TILES && count > 1) {
-        // pixels owned by this shard
-        uint64_t px = 0;
-        for (int t = rank; t < n_tiles; t += count) {
-            int tx = t % A.tiles_x, ty = t / A.tiles_x;
-            int w = std::min(A.tile_size, p->width - tx * A.tile_size), h = std::min(A.tile_size, p->height - ty * A.tile_size);
-            px += (uint64_t)w * h;
-        }
-        ctx->stats.samples = px * (uint64_t)A.n_local_samples;
-    }
+    ctx->stats.samples = pass_samples();
     CU(ctx, cudaEventRecord(ctx->ev1, stream));
     ctx->pending_async = true;
     ctx->pending_stats = stats;
