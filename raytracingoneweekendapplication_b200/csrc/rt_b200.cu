@@ -147,7 +147,9 @@ __device__ __forceinline__ void frame_add(unsigned long long* a, unsigned long l
 #endif
 }
 
-template <bool STATS, bool LITE, bool NEE = false, int WIDTH = 2>
+// MEDIA = false: the instance for scenes without a constant_medium (C1, C2, C4): the free-flight code is not compiled in
+// (like LITE, it costs registers and spills even where it never runs: +1.6 % on C2, +2 % on C1, +3.2 % on C4, +5 % on monkey)
+template <bool STATS, bool LITE, bool NEE = false, int WIDTH = 2, bool MEDIA = true>
 __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT_WIDE_MIN_BLOCKS) render_kernel_v2(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A,
                                                         unsigned long long* __restrict__ accum,
                                                         unsigned long long* __restrict__ counters, Stats* __restrict__ gstats) {
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
 #endif
             Hit hit = tr.hit;
             int medium = -1;
-            if (S.n_media > 0) medium = media_hit<STATS>(S, ray, 0.001f, hit.t, rng, bounce, &st);
+            if (MEDIA && S.n_media > 0) medium = media_hit<STATS>(S, ray, 0.001f, hit.t, rng, bounce, &st);
             bool done = false;
             if (medium < 0 && hit.prim == PRIM_NONE) {
                 L = L + T * v3(S.background);
@@ -796,6 +798,8 @@ static int dev_create(DevCtx** out, const int* device_ids, int n_devices) {
     cudaFuncSetAttribute(render_kernel_v2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel_v2<false, false, false, 2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel_v2<false, true, false, 2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
 #if RT_PARK_STATE  // measurement build: 9 words per thread of parked path state, RT_MIN_BLOCKS blocks per SM
     {
         const int pct = (int)((100 * RT_MIN_BLOCKS * (10 * RT_V2_THREADS * 4 + 2048) + 233471) / 233472);
@@ -1926,7 +1930,8 @@ static int launch_wavefront(DevCtx* ctx, const RenderArgs& A, cudaStream_t strea
 }
 #endif
 
-// The instances of render_kernel_v2: variant 0 plain, 1 LITE, 2 STATS, 3 NEE + LITE, 4 NEE; width 2, 4, 8.
+// The instances of render_kernel_v2: variant 0 plain, 1 LITE, 2 STATS, 3 NEE + LITE, 4 NEE, 5 plain without media code,
+// 6 LITE without media code; width 2, 4, 8 (3-6: binary tree only).
 typedef void (*RenderKernel)(const DevScene, const RenderArgs, unsigned long long*, unsigned long long*, Stats*);
 template <int WIDTH>
 static RenderKernel v2_instance(int variant) {
@@ -1942,6 +1947,8 @@ static int v2_effective_width(int variant, int width) { return variant >= 3 ? 2 
 static RenderKernel v2_kernel(int variant, int width) {
     if (variant == 3) return render_kernel_v2<false, true, true, 2>;
     if (variant == 4) return render_kernel_v2<false, false, true, 2>;
+    if (variant == 5) return render_kernel_v2<false, false, false, 2, false>;
+    if (variant == 6) return render_kernel_v2<false, true, false, 2, false>;
     return width == 8 ? v2_instance<8>(variant) : (width == 4 ? v2_instance<4>(variant) : v2_instance<2>(variant));
 }
 // dynamic shared memory of a wide instance: the traversal stacks, [entry][thread]
@@ -2060,8 +2067,9 @@ static int dev_render(DevCtx* ctx, const rt_render_params* p) {
     const bool lite = ctx->scene_lite && !getenv("RT_B200_NO_LITE");
     const bool want_nee = (p->flags & RT_FLAG_NEE) != 0 && ctx->scene.n_nee_lights > 0;
     const bool want_shadow = (p->flags & RT_FLAG_SHADOWED_POINT_LIGHTS) != 0 && ctx->scene.n_lights > 0;
-    const int variant = (want_nee || want_shadow) ? (lite ? 3 : 4) : (stats ? 2 : (lite ? 1 : 0));
+    int variant = (want_nee || want_shadow) ? (lite ? 3 : 4) : (stats ? 2 : (lite ? 1 : 0));
     const int width = ctx->scene.wide_width ? ctx->scene.wide_width : 2;
+    if (variant <= 1 && width == 2 && ctx->scene.n_media == 0 && !getenv("RT_B200_NO_MEDIA_INSTANCE")) variant += 5;  // no media in this scene
     if (ctx->kernel_version == 2) {
         rc = v2_blocks_per_sm(ctx, variant, width, &bps);
         if (rc != RT_OK) return rc;

@@ -257,3 +257,24 @@ def test_box_bounded_media_take_the_slab_test(built, scene_of, monkeypatch):
     same = np.isclose(a, b, rtol=1e-4, atol=1e-6).all(axis=2).mean()
     assert same >= 0.98, same
     assert np.allclose(a.mean(axis=(0, 1)), b.mean(axis=(0, 1)), rtol=2e-3)
+
+
+@pytest.mark.parametrize("name", ["book1", "cornell", "mesh"])
+def test_the_instance_without_media_code_renders_the_same_bits(built, scene_of, monkeypatch, name):
+    """Scenes without a constant_medium run render_kernel_v2<..., MEDIA=false> (no free-flight code compiled in);
+    RT_B200_NO_MEDIA_INSTANCE=1 forces the general instance: same sums."""
+    sc = scene_of(name)
+    out = []
+    for forced in (False, True):
+        if forced:
+            monkeypatch.setenv("RT_B200_NO_MEDIA_INSTANCE", "1")
+        else:
+            monkeypatch.delenv("RT_B200_NO_MEDIA_INSTANCE", raising=False)
+        c = capi.Context(0)
+        try:
+            c.upload(sc)
+            c.render(192, 108, 6, max_depth=sc.depth, seed=11)
+            out.append(c.accum_download())
+        finally:
+            c.close()
+    assert np.array_equal(out[0], out[1])
