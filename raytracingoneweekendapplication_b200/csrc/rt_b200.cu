@@ -147,9 +147,13 @@ __device__ __forceinline__ void frame_add(unsigned long long* a, unsigned long l
 #endif
 }
 
-// MEDIA = false: the instance for scenes without a constant_medium (C1, C2, C4): the free-flight code is not compiled in
-// (like LITE, it costs registers and spills even where it never runs: +1.6 % on C2, +2 % on C1, +3.2 % on C4, +5 % on monkey)
-template <bool STATS, bool LITE, bool NEE = false, int WIDTH = 2, bool MEDIA = true>
+// FEAT: which rarely needed code the instance carries (like LITE: code that never runs still costs registers and spills).
+//   FEAT_MEDIA          the scene has a constant_medium (without: C1, C2, C4 -- +2 %, +1.9 %, +3.4 %)
+//   FEAT_MEDIA_GENERAL  some boundary is not one static sphere (C3's boxes; without: C5 +3.7 %)
+//   FEAT_SPECULAR       some material is RT_MAT_SPECULAR (without: C5 +0.6 %)
+// The plain binary-tree instances are compiled for the masks of kFeatMasks; a scene runs the smallest one that covers it.
+enum : int { FEAT_MEDIA = 1, FEAT_MEDIA_GENERAL = 2, FEAT_SPECULAR = 4, FEAT_ALL = 7 };
+template <bool STATS, bool LITE, bool NEE = false, int WIDTH = 2, int FEAT = FEAT_ALL>
 __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT_WIDE_MIN_BLOCKS) render_kernel_v2(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A,
                                                         unsigned long long* __restrict__ accum,
                                                         unsigned long long* __restrict__ counters, Stats* __restrict__ gstats) {
@@ -338,7 +342,7 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
 #endif
             Hit hit = tr.hit;
             int medium = -1;
-            if (MEDIA && S.n_media > 0) medium = media_hit<STATS>(S, ray, 0.001f, hit.t, rng, bounce, &st);
+            if ((FEAT & FEAT_MEDIA) && S.n_media > 0) medium = media_hit<STATS, (FEAT & FEAT_MEDIA_GENERAL) != 0>(S, ray, 0.001f, hit.t, rng, bounce, &st);
             bool done = false;
             if (medium < 0 && hit.prim == PRIM_NONE) {
                 L = L + T * v3(S.background);
@@ -365,7 +369,7 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
                 if (m.type != RT_MAT_DIFFUSE_LIGHT && m.type != RT_MAT_EMISSIVE_LIGHT) u4 = rng.draw(bounce, RS_SCATTER);
                 V3 att, emitted;
                 Ray next;
-                const bool scattered = shade_surface(S, m, ray, sf, u4, emitted, att, next);
+                const bool scattered = shade_surface<(FEAT & FEAT_SPECULAR) != 0>(S, m, ray, sf, u4, emitted, att, next);
                 // NEE: a listed emitter reached from a vertex that also sampled the emitters directly shares the
                 // estimate with that sample (balance heuristic)
                 if (NEE && nee_pdf > 0.0f && medium < 0 && sf.nee_light > 0) {
@@ -689,6 +693,7 @@ struct DevCtx {
     uint64_t staged_key = 0;   // fingerprint of the scene whose arena image is in `staging` (0: none)
     size_t staged_bytes = 0;
     int bvh_width = RT_B200_DEFAULT_BVH_WIDTH;
+    int scene_feat = FEAT_ALL;  // FEAT_* bits the uploaded scene needs
     int wide_depth = 0;  // levels of the uploaded wide tree = stack entries a ray can need
     // RT_FLAG_OVERLAP: asynchronous accumulate passes alternate between two streams of the context, each with its own work
     // counter (counters + 4 and + 8), so that the drain of one pass runs while the next takes over the freed SM slots
@@ -798,8 +803,12 @@ static int dev_create(DevCtx** out, const int* device_ids, int n_devices) {
     cudaFuncSetAttribute(render_kernel_v2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(render_kernel_v2<false, false, false, 2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(render_kernel_v2<false, true, false, 2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel_v2<false, false, false, 2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel_v2<false, true, false, 2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel_v2<false, false, false, 2, FEAT_MEDIA>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel_v2<false, true, false, 2, FEAT_MEDIA>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel_v2<false, false, false, 2, FEAT_MEDIA | FEAT_MEDIA_GENERAL>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel_v2<false, true, false, 2, FEAT_MEDIA | FEAT_MEDIA_GENERAL>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
 #if RT_PARK_STATE  // measurement build: 9 words per thread of parked path state, RT_MIN_BLOCKS blocks per SM
     {
         const int pct = (int)((100 * RT_MIN_BLOCKS * (10 * RT_V2_THREADS * 4 + 2048) + 233471) / 233472);
@@ -1528,6 +1537,12 @@ static int upload_scene_impl(DevCtx* ctx, const rt_scene_desc* sc, bool device_b
     ctx->camera = sc->camera;
     ctx->n_materials = sc->n_materials;
     ctx->n_textures = sc->n_textures;
+    ctx->scene_feat = 0;
+    if (sc->n_media > 0) ctx->scene_feat |= FEAT_MEDIA;
+    for (const DevMedium& d : media)
+        if (d.sphere < 0) ctx->scene_feat |= FEAT_MEDIA_GENERAL;
+    for (int i = 0; i < sc->n_materials; i++)
+        if (sc->materials[i].type == RT_MAT_SPECULAR) ctx->scene_feat |= FEAT_SPECULAR;
     ctx->scene_lite = tri.empty() && world_count[PT_TRI] == 0 && sc->n_lights == 0 && !(sc->camera.defocus_angle > 0);
     ctx->cam_w = ctx->cam_h = 0;
     ctx->has_scene = true;
@@ -1930,9 +1945,10 @@ static int launch_wavefront(DevCtx* ctx, const RenderArgs& A, cudaStream_t strea
 }
 #endif
 
-// The instances of render_kernel_v2: variant 0 plain, 1 LITE, 2 STATS, 3 NEE + LITE, 4 NEE, 5 plain without media code,
-// 6 LITE without media code; width 2, 4, 8 (3-6: binary tree only).
+// The instances of render_kernel_v2: variant 0 plain, 1 LITE, 2 STATS, 3 NEE + LITE, 4 NEE; width 2, 4, 8 (3, 4: binary tree
+// only).  Variants 5 + 2 k (plain) and 6 + 2 k (LITE): the binary-tree instance for feature mask kFeatMasks[k].
 typedef void (*RenderKernel)(const DevScene, const RenderArgs, unsigned long long*, unsigned long long*, Stats*);
+static const int kFeatMasks[3] = {0, FEAT_MEDIA, FEAT_MEDIA | FEAT_MEDIA_GENERAL};  // then FEAT_ALL = variants 0 / 1
 template <int WIDTH>
 static RenderKernel v2_instance(int variant) {
     switch (variant) {
@@ -1947,8 +1963,15 @@ static int v2_effective_width(int variant, int width) { return variant >= 3 ? 2 
 static RenderKernel v2_kernel(int variant, int width) {
     if (variant == 3) return render_kernel_v2<false, true, true, 2>;
     if (variant == 4) return render_kernel_v2<false, false, true, 2>;
-    if (variant == 5) return render_kernel_v2<false, false, false, 2, false>;
-    if (variant == 6) return render_kernel_v2<false, true, false, 2, false>;
+    switch (variant) {
+        case 5: return render_kernel_v2<false, false, false, 2, 0>;
+        case 6: return render_kernel_v2<false, true, false, 2, 0>;
+        case 7: return render_kernel_v2<false, false, false, 2, FEAT_MEDIA>;
+        case 8: return render_kernel_v2<false, true, false, 2, FEAT_MEDIA>;
+        case 9: return render_kernel_v2<false, false, false, 2, FEAT_MEDIA | FEAT_MEDIA_GENERAL>;
+        case 10: return render_kernel_v2<false, true, false, 2, FEAT_MEDIA | FEAT_MEDIA_GENERAL>;
+        default: break;
+    }
     return width == 8 ? v2_instance<8>(variant) : (width == 4 ? v2_instance<4>(variant) : v2_instance<2>(variant));
 }
 // dynamic shared memory of a wide instance: the traversal stacks, [entry][thread]
@@ -2069,7 +2092,10 @@ static int dev_render(DevCtx* ctx, const rt_render_params* p) {
     const bool want_shadow = (p->flags & RT_FLAG_SHADOWED_POINT_LIGHTS) != 0 && ctx->scene.n_lights > 0;
     int variant = (want_nee || want_shadow) ? (lite ? 3 : 4) : (stats ? 2 : (lite ? 1 : 0));
     const int width = ctx->scene.wide_width ? ctx->scene.wide_width : 2;
-    if (variant <= 1 && width == 2 && ctx->scene.n_media == 0 && !getenv("RT_B200_NO_MEDIA_INSTANCE")) variant += 5;  // no media in this scene
+    // the smallest compiled feature mask that covers the scene (RT_B200_NO_MEDIA_INSTANCE=1: always the general instance)
+    if (variant <= 1 && width == 2 && !getenv("RT_B200_NO_MEDIA_INSTANCE"))
+        for (int k = 0; k < 3; k++)
+            if ((ctx->scene_feat & ~kFeatMasks[k]) == 0) { variant += 5 + 2 * k; break; }
     if (ctx->kernel_version == 2) {
         rc = v2_blocks_per_sm(ctx, variant, width, &bps);
         if (rc != RT_OK) return rc;

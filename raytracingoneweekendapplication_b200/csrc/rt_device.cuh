@@ -596,7 +596,9 @@ __device__ __noinline__ bool boundary_pair_box(const float4* __restrict__ bx, co
 // A boundary that is one static sphere (both media of the book-2 scene) takes ONE quadratic:
 // sphere::hit over the universe returns the smaller root, and over (t1 + 1e-4, inf) the larger
 // one if it lies beyond t1 + 1e-4 (sphere.h:44-49).
-template <bool STATS>
+// GENERAL = false: every boundary of the scene is one static sphere (both media of C5); the out-of-line box / generic
+// paths are then not even call sites -- they cost the caller registers and spills where they never run (C5 +3.7 %).
+template <bool STATS, bool GENERAL = true>
 __device__ __forceinline__ int media_hit(const DevScene& S, const Ray& ray, float tmin, float& t_hit, const Rng& rng,
                                          uint32_t bounce, Stats* st) {
     int which = -1;
@@ -632,6 +634,8 @@ __device__ __forceinline__ int media_hit(const DevScene& S, const Ray& ray, floa
                 t2 = k + sq;
             }
             if (!(t2 > t1 + 0.0001f)) continue;
+        } else if (!GENERAL) {
+            continue;  // instance for scenes whose boundaries are all single spheres: no call site of the two below
         } else if (md.box >= 0) {
             if (!boundary_pair_box(S.media_box + 4 * (size_t)md.box, ray, t1, t2)) continue;
         } else {
@@ -979,6 +983,9 @@ __device__ __noinline__ V3 specular_direction(V3 unit, V3 refl, V3 ruv, V3 norma
 // vec3.h:107-115, the normalised incoming direction and its mirror image -- and differ in a
 // handful of instructions each: the material switch is the most divergent code of the shade
 // phase, and its size is instruction-cache footprint.
+// SPECULAR = false: no material of the scene is RT_MAT_SPECULAR (the reference's `specular` class, unused by its own
+// scenes): no call site of specular_direction.
+template <bool SPECULAR = true>
 __device__ __forceinline__ bool shade_surface(const DevScene& S, const DevMaterial& m, const Ray& in, const Surface& sf, float4 u4,
                                               V3& emitted, V3& attenuation, Ray& out) {
     out.o = sf.p;
@@ -1031,7 +1038,7 @@ __device__ __forceinline__ bool shade_surface(const DevScene& S, const DevMateri
         }
         return true;
     }
-    out.d = specular_direction(unit, refl, ruv, sf.normal, m.param);  // RT_MAT_SPECULAR
+    if (SPECULAR) out.d = specular_direction(unit, refl, ruv, sf.normal, m.param);  // RT_MAT_SPECULAR
     return true;
 }
 
