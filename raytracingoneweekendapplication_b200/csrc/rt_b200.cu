@@ -151,8 +151,9 @@ __device__ __forceinline__ void frame_add(unsigned long long* a, unsigned long l
 //   FEAT_MEDIA          the scene has a constant_medium (without: C1, C2, C4 -- +2 %, +1.9 %, +3.4 %)
 //   FEAT_MEDIA_GENERAL  some boundary is not one static sphere (C3's boxes; without: C5 +3.7 %)
 //   FEAT_SPECULAR       some material is RT_MAT_SPECULAR (without: C5 +0.6 %)
+//   FEAT_MSPHERE        the world holds a moving sphere (C5 has one)
 // The plain binary-tree instances are compiled for the masks of kFeatMasks; a scene runs the smallest one that covers it.
-enum : int { FEAT_MEDIA = 1, FEAT_MEDIA_GENERAL = 2, FEAT_SPECULAR = 4, FEAT_ALL = 7 };
+enum : int { FEAT_MEDIA = 1, FEAT_MEDIA_GENERAL = 2, FEAT_SPECULAR = 4, FEAT_MSPHERE = 8, FEAT_ALL = 15 };
 template <bool STATS, bool LITE, bool NEE = false, int WIDTH = 2, int FEAT = FEAT_ALL>
 __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT_WIDE_MIN_BLOCKS) render_kernel_v2(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A,
                                                         unsigned long long* __restrict__ accum,
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
                 }
                 if (state == LANE_TRAVERSE && !tr.wants_node()) {
                     if (!tr.done()) {
-                        tr.template leaf_step<STATS, LITE>(S, ray, rc, 0.001f, origin_prim, stack, &st);
+                        tr.template leaf_step<STATS, LITE, (FEAT & FEAT_MSPHERE) != 0>(S, ray, rc, 0.001f, origin_prim, stack, &st);
                         if (STATS) {
                             atomicAdd(hist + (n_leaf ? 64 : 0) + min(seg_steps, 63u), 1ull);
                             n_leaf++;
@@ -805,8 +806,8 @@ static int dev_create(DevCtx** out, const int* device_ids, int n_devices) {
     cudaFuncSetAttribute(render_kernel_v2<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, false, false, 2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, true, false, 2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(render_kernel_v2<false, false, false, 2, FEAT_MEDIA>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(render_kernel_v2<false, true, false, 2, FEAT_MEDIA>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel_v2<false, false, false, 2, FEAT_MEDIA | FEAT_MSPHERE>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(render_kernel_v2<false, true, false, 2, FEAT_MEDIA | FEAT_MSPHERE>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, false, false, 2, FEAT_MEDIA | FEAT_MEDIA_GENERAL>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, true, false, 2, FEAT_MEDIA | FEAT_MEDIA_GENERAL>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
 #if RT_PARK_STATE  // measurement build: 9 words per thread of parked path state, RT_MIN_BLOCKS blocks per SM
@@ -1543,6 +1544,7 @@ static int upload_scene_impl(DevCtx* ctx, const rt_scene_desc* sc, bool device_b
         if (d.sphere < 0) ctx->scene_feat |= FEAT_MEDIA_GENERAL;
     for (int i = 0; i < sc->n_materials; i++)
         if (sc->materials[i].type == RT_MAT_SPECULAR) ctx->scene_feat |= FEAT_SPECULAR;
+    if (world_count[PT_MSPHERE] > 0 || !msph.empty()) ctx->scene_feat |= FEAT_MSPHERE;
     ctx->scene_lite = tri.empty() && world_count[PT_TRI] == 0 && sc->n_lights == 0 && !(sc->camera.defocus_angle > 0);
     ctx->cam_w = ctx->cam_h = 0;
     ctx->has_scene = true;
@@ -1948,7 +1950,7 @@ static int launch_wavefront(DevCtx* ctx, const RenderArgs& A, cudaStream_t strea
 // The instances of render_kernel_v2: variant 0 plain, 1 LITE, 2 STATS, 3 NEE + LITE, 4 NEE; width 2, 4, 8 (3, 4: binary tree
 // only).  Variants 5 + 2 k (plain) and 6 + 2 k (LITE): the binary-tree instance for feature mask kFeatMasks[k].
 typedef void (*RenderKernel)(const DevScene, const RenderArgs, unsigned long long*, unsigned long long*, Stats*);
-static const int kFeatMasks[3] = {0, FEAT_MEDIA, FEAT_MEDIA | FEAT_MEDIA_GENERAL};  // then FEAT_ALL = variants 0 / 1
+static const int kFeatMasks[3] = {0, FEAT_MEDIA | FEAT_MSPHERE, FEAT_MEDIA | FEAT_MEDIA_GENERAL};  // C1/C2/C4, C5, C3; then FEAT_ALL = variants 0 / 1
 template <int WIDTH>
 static RenderKernel v2_instance(int variant) {
     switch (variant) {
@@ -1966,8 +1968,8 @@ static RenderKernel v2_kernel(int variant, int width) {
     switch (variant) {
         case 5: return render_kernel_v2<false, false, false, 2, 0>;
         case 6: return render_kernel_v2<false, true, false, 2, 0>;
-        case 7: return render_kernel_v2<false, false, false, 2, FEAT_MEDIA>;
-        case 8: return render_kernel_v2<false, true, false, 2, FEAT_MEDIA>;
+        case 7: return render_kernel_v2<false, false, false, 2, FEAT_MEDIA | FEAT_MSPHERE>;
+        case 8: return render_kernel_v2<false, true, false, 2, FEAT_MEDIA | FEAT_MSPHERE>;
         case 9: return render_kernel_v2<false, false, false, 2, FEAT_MEDIA | FEAT_MEDIA_GENERAL>;
         case 10: return render_kernel_v2<false, true, false, 2, FEAT_MEDIA | FEAT_MEDIA_GENERAL>;
         default: break;

@@ -335,14 +335,30 @@ __device__ __forceinline__ void hit_tri(float4 t0, float4 t1, float4 t2, const R
 // LITE: the scene has no triangles (and, elsewhere, no point lights and no defocus): the
 // production kernel is also compiled without those features, because in one megakernel every
 // feature costs every scene registers and instruction-cache (C5 +4 % without them).
-template <bool STATS, bool LITE = false>
+// MSPH = false: the scene has no moving sphere (instance without that code).
+template <bool STATS, bool LITE = false, bool MSPH = true>
 __device__ __forceinline__ void hit_prim(const DevScene& S, uint32_t type, uint32_t idx, const Ray& ray, float inv_a, float tmin,
                                          uint32_t origin_prim, Hit& hit, Stats* st) {
     uint32_t prim = (type << 28) | idx;
-    if (type == PT_SPHERE) {
+    if (MSPH ? type <= PT_MSPHERE : type == PT_SPHERE) {
+        // static and moving spheres share ONE inlined copy of the test (and one call site of the FP64 roots): only the
+        // fetch of the centre differs (sphere.h:33 center.at(r.time())) -- two copies cost C5, which has one moving
+        // sphere, 4 % (round 2)
         if (STATS) st->sphere_tests++;
-        float4 s = ldg4_hint<RT_PRIM_HINT>(S.sph + idx);
-        hit_sphere<STATS>(v3(s), s.w, S.sph_d + 4 * (size_t)idx, false, prim == origin_prim, ray, inv_a, tmin, prim, hit, st);
+        float4 s;
+        const double* cd;
+        const bool moving = MSPH && type == PT_MSPHERE;
+        if (!moving) {
+            s = ldg4_hint<RT_PRIM_HINT>(S.sph + idx);
+            cd = S.sph_d + 4 * (size_t)idx;
+        } else {
+            const float4* m = S.msph + 2 * (size_t)idx;
+            const float4 a = ldg4(m), b = ldg4(m + 1);
+            const V3 c = fma3(ray.time, v3(b), v3(a));
+            s = make_float4(c.x, c.y, c.z, a.w);
+            cd = S.msph_d + 8 * (size_t)idx;
+        }
+        hit_sphere<STATS>(v3(s), s.w, cd, moving, prim == origin_prim, ray, inv_a, tmin, prim, hit, st);
     } else if (type == PT_QUAD) {
         if (STATS) st->quad_tests++;
         if (prim == origin_prim) return;  // a ray leaving a planar primitive cannot hit it again
@@ -353,12 +369,6 @@ __device__ __forceinline__ void hit_prim(const DevScene& S, uint32_t type, uint3
         if (prim == origin_prim) return;
         const float4* t = S.tri + 3 * (size_t)idx;
         hit_tri(ldg4(t), ldg4(t + 1), ldg4(t + 2), ray, tmin, prim, hit);
-    } else {
-        if (STATS) st->sphere_tests++;
-        const float4* m = S.msph + 2 * (size_t)idx;
-        float4 a = ldg4(m), b = ldg4(m + 1);
-        V3 c = fma3(ray.time, v3(b), v3(a));  // sphere.h:33 center.at(r.time())
-        hit_sphere<STATS>(c, a.w, S.msph_d + 8 * (size_t)idx, true, prim == origin_prim, ray, inv_a, tmin, prim, hit, st);
     }
 }
 
@@ -505,12 +515,12 @@ struct Trav {
         else pop(stack);
     }
 
-    template <bool STATS, bool LITE = false, class Stack>
+    template <bool STATS, bool LITE = false, bool MSPH = true, class Stack>
     __device__ __forceinline__ void leaf(const DevScene& S, const Ray& ray, const RayConst& rc, float tmin, uint32_t origin_prim,
                                          Stack stack, Stats* st) {
         uint32_t v = ~(uint32_t)cur;
         uint32_t type = v >> 28, cnt = ((v >> 25) & 7u) + 1u, first = v & 0x1ffffffu;
-        for (uint32_t i = 0; i < cnt; i++) hit_prim<STATS, LITE>(S, type, first + i, ray, rc.inv_a, tmin, origin_prim, hit, st);
+        for (uint32_t i = 0; i < cnt; i++) hit_prim<STATS, LITE, MSPH>(S, type, first + i, ray, rc.inv_a, tmin, origin_prim, hit, st);
         pop(stack);
     }
 
@@ -518,10 +528,10 @@ struct Trav {
     __device__ __forceinline__ void node_step(const DevScene& S, const Ray&, const RayConst& rc, float tmin, Stack stack, Stats* st) {
         interior<STATS>(S, rc, tmin, stack, st, nullptr);
     }
-    template <bool STATS, bool LITE, class Stack>
+    template <bool STATS, bool LITE, bool MSPH = true, class Stack>
     __device__ __forceinline__ void leaf_step(const DevScene& S, const Ray& ray, const RayConst& rc, float tmin, uint32_t origin_prim,
                                               Stack stack, Stats* st) {
-        leaf<STATS, LITE>(S, ray, rc, tmin, origin_prim, stack, st);
+        leaf<STATS, LITE, MSPH>(S, ray, rc, tmin, origin_prim, stack, st);
     }
 };
 

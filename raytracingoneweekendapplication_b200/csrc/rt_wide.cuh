@@ -213,7 +213,7 @@ struct TravW {
     }
 
     // every pending leaf child of this lane's node: hittable_list.h:22-35 over the leaf's primitives
-    template <bool STATS, bool LITE, class Stack>
+    template <bool STATS, bool LITE, bool MSPH = true, class Stack>
     __device__ __forceinline__ void leaf_step(const DevScene& S, const Ray& ray, const RayConstW& rc, float tmin, uint32_t origin_prim,
                                               const Stack&, Stats* st) {
         const int32_t* refs = S.wrefs + (size_t)W * (tgrp >> 8);
