@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
                     sf.nee_light = 0;
                     origin_prim = PRIM_NONE;
                 } else {
-                    complete_hit(S, ray, hit, sf, false);
+                    complete_hit<LITE, (FEAT & FEAT_MSPHERE) != 0>(S, ray, hit, sf, false);
                     origin_prim = hit.prim;
                 }
                 const DevMaterial& m = S.mats[sf.material];

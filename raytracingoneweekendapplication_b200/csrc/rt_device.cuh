@@ -807,6 +807,8 @@ __device__ __noinline__ void refine_sphere_hit(double cx, double cy, double cz, 
     outward = v3((float)((px - cx) * inv_r), (float)((py - cy) * inv_r), (float)((pz - cz) * inv_r));  // sphere.h:52
 }
 
+// LITE / MSPH as in hit_prim: the instance for scenes without triangles / without moving spheres has none of their code.
+template <bool LITE = false, bool MSPH = true>
 __device__ __forceinline__ void complete_hit(const DevScene& S, const Ray& ray, const Hit& hit, Surface& sf, bool want_uv) {
     uint32_t type = hit.prim >> 28, idx = hit.prim & 0x0fffffffu;
     sf.t = hit.t;
@@ -821,7 +823,7 @@ __device__ __forceinline__ void complete_hit(const DevScene& S, const Ray& ray, 
         // normal, so that a far-away small sphere still gets a normal good to FP32 rounding.
         int4 sh;
         double cx, cy, cz, rr;
-        if (type == PT_SPHERE) {
+        if (!MSPH || type == PT_SPHERE) {
             const double* cd = S.sph_d + 4 * (size_t)idx;
             cx = cd[0]; cy = cd[1]; cz = cd[2]; rr = cd[3];
             sh = __ldg(S.sph_sh + idx);
@@ -857,7 +859,7 @@ __device__ __forceinline__ void complete_hit(const DevScene& S, const Ray& ray, 
             }
             sphere_uv(n, sf.u, sf.v);
         }
-    } else if (type == PT_QUAD) {
+    } else if (LITE || type == PT_QUAD) {
         outward = v3(ldg4(S.quad + 3 * (size_t)idx));
         int4 sh = __ldg(S.quad_sh + idx);
         sf.material = sh.x;
