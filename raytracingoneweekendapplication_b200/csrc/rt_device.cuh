@@ -726,7 +726,29 @@ __device__ __forceinline__ float perlin_turb(const DevScene& S, int pidx, V3 p, 
     return fabsf(accum);
 }
 
-__device__ __noinline__ V3 tex_value_general(const DevScene& S, int tex, float u, float v, V3 p) {
+__device__ __forceinline__ void sphere_uv(V3 n, float& u, float& v) {  // sphere.h:67-73
+    const float pi = 3.14159265358979323846f;
+    float theta = acosf(fminf(fmaxf(-n.y, -1.0f), 1.0f));
+    float phi = atan2f(-n.z, n.x) + pi;
+    u = phi / (2.0f * pi);
+    v = theta / pi;
+}
+
+// uv_xf > -2: the hit is on a sphere whose (u, v) have not been computed: `outward` is its outward unit normal and
+// uv_xf its transform (-1 none).  sphere.h:67-73 (an acos, an atan2 and a rotation back to object space) then runs HERE,
+// out of line and only for the textures that read (u, v) -- the hot kernel body carries none of it (instruction cache).
+__device__ __noinline__ V3 tex_value_general(const DevScene& S, int tex, float u, float v, V3 p, int uv_xf, V3 outward) {
+    auto resolve_uv = [&]() {
+        if (uv_xf <= -2) return;
+        V3 n = outward;
+        if (uv_xf >= 0) {  // back to object space: R^T n
+            const float* R = S.xrot + 9 * (size_t)uv_xf;
+            n = v3(R[0] * outward.x + R[3] * outward.y + R[6] * outward.z, R[1] * outward.x + R[4] * outward.y + R[7] * outward.z,
+                   R[2] * outward.x + R[5] * outward.y + R[8] * outward.z);
+        }
+        sphere_uv(n, u, v);
+        uv_xf = -2;
+    };
     // checker textures select a child and recurse (texture.h:42-50, 66-76): iterate instead
     for (int level = 0; level < 16; level++) {
         const DevTexture& t = S.texs[tex];
@@ -736,11 +758,13 @@ __device__ __noinline__ V3 tex_value_general(const DevScene& S, int tex, float u
             int xi = (int)floorf(t.scale * p.x), yi = (int)floorf(t.scale * p.y), zi = (int)floorf(t.scale * p.z);
             tex = ((xi + yi + zi) % 2 == 0) ? t.a : t.b;
         } else if (t.type == RT_TEX_CHECKER_TRIANGLE) {
+            resolve_uv();
             v = 1.0f - v;  // texture.h:68: flipped, and the flipped value is what the child sees
             int ui = (int)roundf(t.scale * u * 10.0f), vi = (int)roundf(t.scale * v * 10.0f);
             tex = ((ui + vi) % 2 == 0) ? t.a : t.b;
         } else if (t.type == RT_TEX_IMAGE) {
             if (t.a < 0) return v3(0.0f, 1.0f, 1.0f);  // texture.h:92
+            resolve_uv();
             const DevImage& im = S.images[t.a];
             float uc = fminf(fmaxf(u, 0.0f), 1.0f);
             float vc = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
@@ -760,10 +784,10 @@ __device__ __noinline__ V3 tex_value_general(const DevScene& S, int tex, float u
 }
 
 // solid_color is by far the most common texture: keep it inline, send the rest out of line
-__device__ __forceinline__ V3 tex_value(const DevScene& S, int tex, float u, float v, V3 p) {
+__device__ __forceinline__ V3 tex_value(const DevScene& S, int tex, float u, float v, V3 p, int uv_xf = -2, V3 outward = V3{0.0f, 0.0f, 0.0f}) {
     const DevTexture& t = S.texs[tex];
     if (t.type == RT_TEX_SOLID) return v3(t.color);
-    return tex_value_general(S, tex, u, v, p);
+    return tex_value_general(S, tex, u, v, p, uv_xf, outward);
 }
 
 // ---------------------------------------------------------------------------------
@@ -776,16 +800,9 @@ struct Surface {
     int material;
     int prim_id;
     int nee_light;  // > 0: this surface is emitter number nee_light - 1 of the next-event list
+    int uv_xf = -2;  // -2: (u, v) are valid; >= -1: a sphere hit whose (u, v) the texture lookup computes on demand (its transform)
     bool front;
 };
-
-__device__ __forceinline__ void sphere_uv(V3 n, float& u, float& v) {  // sphere.h:67-73
-    const float pi = 3.14159265358979323846f;
-    float theta = acosf(fminf(fmaxf(-n.y, -1.0f), 1.0f));
-    float phi = atan2f(-n.z, n.x) + pi;
-    u = phi / (2.0f * pi);
-    v = theta / pi;
-}
 
 // The accepted sphere hit re-solved in double (sphere.h:33-52 verbatim); out of line, once per
 // sphere hit.
@@ -849,7 +866,8 @@ __device__ __forceinline__ void complete_hit(const DevScene& S, const Ray& ray, 
         sf.material = sh.x;
         sf.prim_id = sh.z;
         sf.u = sf.v = 0.0f;
-        if (want_uv || (sh.x >= 0 && S.mats[sh.x].needs_uv)) {
+        sf.uv_xf = sh.y < 0 ? -1 : sh.y;  // (u, v) on demand: tex_value_general
+        if (want_uv) {                    // the probes want them here
             V3 n = outward;
             if (sh.y >= 0) {  // back to object space: R^T n
                 const float* R = S.xrot + 9 * (size_t)sh.y;
@@ -858,6 +876,7 @@ __device__ __forceinline__ void complete_hit(const DevScene& S, const Ray& ray, 
                        R[2] * outward.x + R[5] * outward.y + R[8] * outward.z);
             }
             sphere_uv(n, sf.u, sf.v);
+            sf.uv_xf = -2;
         }
     } else if (LITE || type == PT_QUAD) {
         outward = v3(ldg4(S.quad + 3 * (size_t)idx));
@@ -1004,7 +1023,7 @@ __device__ __forceinline__ bool shade_surface(const DevScene& S, const DevMateri
     out.time = in.time;
     out.d = sf.normal;
     V3 texc = v3(0, 0, 0);
-    if (m.tex >= 0) texc = tex_value(S, m.tex, sf.u, sf.v, sf.p);
+    if (m.tex >= 0) texc = tex_value(S, m.tex, sf.u, sf.v, sf.p, sf.uv_xf, sf.front ? sf.normal : -sf.normal);
     emitted = v3(0, 0, 0);
     attenuation = texc;
     if (m.type == RT_MAT_DIFFUSE_LIGHT || m.type == RT_MAT_EMISSIVE_LIGHT) {  // material.h:17-19, 99-101, 116-118
@@ -1056,7 +1075,7 @@ __device__ __forceinline__ bool shade_surface(const DevScene& S, const DevMateri
 
 // kept for the probes and the first kernel version: the same thing in two calls
 __device__ __forceinline__ V3 mat_emitted(const DevScene& S, const DevMaterial& m, const Surface& sf) {
-    if (m.type == RT_MAT_DIFFUSE_LIGHT || m.type == RT_MAT_EMISSIVE_LIGHT) return tex_value(S, m.tex, sf.u, sf.v, sf.p);
+    if (m.type == RT_MAT_DIFFUSE_LIGHT || m.type == RT_MAT_EMISSIVE_LIGHT) return tex_value(S, m.tex, sf.u, sf.v, sf.p, sf.uv_xf, sf.front ? sf.normal : -sf.normal);
     return v3(0, 0, 0);
 }
 __device__ __forceinline__ bool mat_scatter(const DevScene& S, const DevMaterial& m, const Ray& in, const Surface& sf, float4 u4,
