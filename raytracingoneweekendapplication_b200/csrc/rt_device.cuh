@@ -806,8 +806,12 @@ struct Surface {
 
 // The accepted sphere hit re-solved in double (sphere.h:33-52 verbatim); out of line, once per
 // sphere hit.
-__device__ __noinline__ void refine_sphere_hit(double cx, double cy, double cz, double rr, const Ray& ray, float t_approx, float& t_out,
+__device__ __noinline__ void refine_sphere_hit(const double* __restrict__ cd, bool moving, const Ray& ray, float t_approx, float& t_out,
                                                V3& p_out, V3& outward) {
+    // the FP64 record is read HERE, not by the caller: the common FP32 completion then holds no doubles at all
+    double cx = cd[0], cy = cd[1], cz = cd[2];
+    const double rr = cd[3];
+    if (moving) { cx += (double)ray.time * cd[4]; cy += (double)ray.time * cd[5]; cz += (double)ray.time * cd[6]; }
     double ox = cx - (double)ray.o.x, oy = cy - (double)ray.o.y, oz = cz - (double)ray.o.z;
     double dx = ray.d.x, dy = ray.d.y, dz = ray.d.z;
     double a = dx * dx + dy * dy + dz * dz;
@@ -839,28 +843,31 @@ __device__ __forceinline__ void complete_hit(const DevScene& S, const Ray& ray, 
         // FP32 traversal fixes WHICH root of WHICH sphere, the FP64 pass fixes t, p and the
         // normal, so that a far-away small sphere still gets a normal good to FP32 rounding.
         int4 sh;
-        double cx, cy, cz, rr;
-        if (!MSPH || type == PT_SPHERE) {
-            const double* cd = S.sph_d + 4 * (size_t)idx;
-            cx = cd[0]; cy = cd[1]; cz = cd[2]; rr = cd[3];
+        float4 s;          // centre and radius in FP32 (the device record the traversal tested)
+        const double* cd;  // the same in double, read only by the refinement
+        const bool moving = MSPH && type != PT_SPHERE;
+        if (!moving) {
+            s = ldg4(S.sph + idx);
+            cd = S.sph_d + 4 * (size_t)idx;
             sh = __ldg(S.sph_sh + idx);
         } else {
-            const double* cd = S.msph_d + 8 * (size_t)idx;
-            cx = cd[0] + (double)ray.time * cd[4]; cy = cd[1] + (double)ray.time * cd[5]; cz = cd[2] + (double)ray.time * cd[6];
-            rr = cd[3];
+            const float4* m = S.msph + 2 * (size_t)idx;
+            const float4 a = ldg4(m), b = ldg4(m + 1);
+            const V3 c = fma3(ray.time, v3(b), v3(a));  // sphere.h:33 center.at(r.time())
+            s = make_float4(c.x, c.y, c.z, a.w);
+            cd = S.msph_d + 8 * (size_t)idx;
             sh = __ldg(S.msph_sh + idx);
         }
         // FP32 suffices unless the sphere is small relative to its distance (the FP32 hit point is
         // only good to ulp(|p|), which the normal magnifies by 1/r) or the ray starts near the
         // surface of a big sphere (cancellation in |oc|^2 - r^2)
         {
-            const float fcx = (float)cx, fcy = (float)cy, fcz = (float)cz, fr = (float)rr;
-            V3 oc = v3(fcx, fcy, fcz) - ray.o;
-            float oc2 = dot(oc, oc), r2 = fr * fr;
+            V3 oc = v3(s) - ray.o;
+            float oc2 = dot(oc, oc), r2 = s.w * s.w;
             if (want_uv || oc2 > 64.0f * r2 || fabsf(oc2 - r2) < 0.125f * r2) {
-                refine_sphere_hit(cx, cy, cz, rr, ray, hit.t, sf.t, sf.p, outward);
+                refine_sphere_hit(cd, moving, ray, hit.t, sf.t, sf.p, outward);
             } else {
-                outward = (1.0f / fr) * (sf.p - v3(fcx, fcy, fcz));  // sphere.h:52
+                outward = __frcp_rn(s.w) * (sf.p - v3(s));  // sphere.h:52
             }
         }
         sf.material = sh.x;
