@@ -128,12 +128,12 @@ struct TravSel { using Trav = TravW<WIDTH>; using RayConst = RayConstW; };
 template <>
 struct TravSel<2> { using Trav = rtdev::Trav; using RayConst = rtdev::RayConst; };
 
+#ifndef RT_PARK_STATE
+#define RT_PARK_STATE 0  // measured: -2.3 % on C5; stays off
+#endif
 // One 64-bit RED into the frame.  RT_FRAME_HINT 1: with an L2 evict_first policy -- the frame (265 MB at 4K) streams through
 // the 126 MB L2 once per pass and would otherwise push out the lines that are re-used: the local-memory stacks and spills
 // (119 MB allocated at 32 warps per SM) and the scene.
-#ifndef RT_PARK_STATE
-#define RT_PARK_STATE 0
-#endif
 #ifndef RT_FRAME_HINT
 #define RT_FRAME_HINT 0  // measured: -0.5 % on C5, -3 % on C3 (profiles/r2_frame_hint_ab.txt); stays off
 #endif
