@@ -152,12 +152,17 @@ __device__ __forceinline__ void frame_add(unsigned long long* a, unsigned long l
 //   FEAT_MEDIA_GENERAL  some boundary is not one static sphere (C3's boxes; without: C5 +3.7 %)
 //   FEAT_SPECULAR       some material is RT_MAT_SPECULAR (without: C5 +0.6 %)
 //   FEAT_MSPHERE        the world holds a moving sphere (C5 has one)
-// The plain binary-tree instances are compiled for the masks of kFeatMasks; a scene runs the smallest one that covers it.
-enum : int { FEAT_MEDIA = 1, FEAT_MEDIA_GENERAL = 2, FEAT_SPECULAR = 4, FEAT_MSPHERE = 8, FEAT_ALL = 15 };
+//   FEAT_TRI / FEAT_LIGHTS / FEAT_DEFOCUS   triangles / point lights / defocus blur: what LITE = true removes together;
+//                       a LITE = false instance carries only those of the three its mask names (C1: defocus only,
+//                       C4: triangles and point lights)
+// The plain binary-tree instances are compiled for the masks of kInstances; a scene runs the first one that covers it.
+enum : int { FEAT_MEDIA = 1, FEAT_MEDIA_GENERAL = 2, FEAT_SPECULAR = 4, FEAT_MSPHERE = 8, FEAT_TRI = 16, FEAT_LIGHTS = 32,
+             FEAT_DEFOCUS = 64, FEAT_ALL = 127 };
 template <bool STATS, bool LITE, bool NEE = false, int WIDTH = 2, int FEAT = FEAT_ALL>
 __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT_WIDE_MIN_BLOCKS) render_kernel_v2(const __grid_constant__ DevScene S, const __grid_constant__ RenderArgs A,
                                                         unsigned long long* __restrict__ accum,
                                                         unsigned long long* __restrict__ counters, Stats* __restrict__ gstats) {
+    constexpr bool NO_TRI = LITE || !(FEAT & FEAT_TRI), NO_DEFOCUS = LITE || !(FEAT & FEAT_DEFOCUS), LIGHTS = !LITE && (FEAT & FEAT_LIGHTS);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     Stats st;
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
                     rng.pixel = (uint32_t)(py * A.width + px);
                     rng.sample = (uint32_t)(A.spp_begin + A.sample_offset + (seg_s0 + (int)(e >> 5)) * A.sample_stride);
                     if (A.compact) lane_slot[threadIdx.x] = slot_base + ((e >> 3) & 3u) * (unsigned)A.tile_size + (e & 7u);
-                    ray = camera_ray<LITE>(S, px, py, rng);
+                    ray = camera_ray<NO_DEFOCUS>(S, px, py, rng);
                     L = v3(0, 0, 0);
                     T = v3(1, 1, 1);
                     bounce = 0;
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
                 }
                 if (state == LANE_TRAVERSE && !tr.wants_node()) {
                     if (!tr.done()) {
-                        tr.template leaf_step<STATS, LITE, (FEAT & FEAT_MSPHERE) != 0>(S, ray, rc, 0.001f, origin_prim, stack, &st);
+                        tr.template leaf_step<STATS, NO_TRI, (FEAT & FEAT_MSPHERE) != 0>(S, ray, rc, 0.001f, origin_prim, stack, &st);
                         if (STATS) {
                             atomicAdd(hist + (n_leaf ? 64 : 0) + min(seg_steps, 63u), 1ull);
                             n_leaf++;
@@ -362,7 +367,7 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
                     sf.nee_light = 0;
                     origin_prim = PRIM_NONE;
                 } else {
-                    complete_hit<LITE, (FEAT & FEAT_MSPHERE) != 0>(S, ray, hit, sf, false);
+                    complete_hit<NO_TRI, (FEAT & FEAT_MSPHERE) != 0>(S, ray, hit, sf, false);
                     origin_prim = hit.prim;
                 }
                 const DevMaterial& m = S.mats[sf.material];
@@ -383,7 +388,7 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
                 if (!scattered) {
                     done = true;
                 } else {
-                    if (!LITE && S.n_lights > 0) {
+                    if (LIGHTS && S.n_lights > 0) {
                         if (NEE && A.shadow_point_lights) L = L + T * att * point_lighting_shadowed<WIDTH>(S, sf.p, sf.normal, origin_prim, ray.time);
                         else L = L + T * att * point_lighting(S, sf.p, sf.normal);
                     }
@@ -438,6 +443,24 @@ __global__ void __launch_bounds__(RT_V2_THREADS, WIDTH == 2 ? RT_MIN_BLOCKS : RT
 #ifdef RT_B200_ALT_KERNELS
 #include "rt_kernel_v3.cuh"
 #endif
+
+// The compiled feature instances of the plain binary-tree kernel (see FEAT_* above); variant 5 + k of the dispatch below.
+typedef void (*RenderKernel)(const DevScene, const RenderArgs, unsigned long long*, unsigned long long*, Stats*);
+struct FeatInstance {
+    bool lite;  // the scene must be LITE (no triangles, point lights, defocus) for lite = true
+    int feat;   // FEAT_* bits the instance carries
+    RenderKernel kernel;
+};
+#define RT_INSTANCE(lite, feat) {lite, feat, render_kernel_v2<false, lite, false, 2, (feat)>}
+static const FeatInstance kInstances[] = {
+    RT_INSTANCE(true, 0),                                                   // C2: quads, nothing else
+    RT_INSTANCE(true, FEAT_MEDIA | FEAT_MSPHERE),                           // C5: media bounded by spheres, a moving sphere
+    RT_INSTANCE(true, FEAT_MEDIA | FEAT_MEDIA_GENERAL),                     // C3: media bounded by boxes
+    RT_INSTANCE(false, FEAT_DEFOCUS),                                       // C1: defocus blur, nothing else
+    RT_INSTANCE(false, FEAT_TRI | FEAT_LIGHTS),                             // C4: triangles and point lights
+};
+#undef RT_INSTANCE
+constexpr int kNumInstances = (int)(sizeof(kInstances) / sizeof(kInstances[0]));
 
 // one ray through whichever acceleration structure the scene was uploaded with (test kernels)
 __device__ __forceinline__ void traverse_uploaded(const DevScene& S, const Ray& ray, float tmin, float tmax, Hit& hit) {
@@ -804,12 +827,7 @@ static int dev_create(DevCtx** out, const int* device_ids, int n_devices) {
     cudaFuncSetAttribute(render_kernel_v2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(render_kernel_v2<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(render_kernel_v2<false, false, false, 2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(render_kernel_v2<false, true, false, 2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(render_kernel_v2<false, false, false, 2, FEAT_MEDIA | FEAT_MSPHERE>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(render_kernel_v2<false, true, false, 2, FEAT_MEDIA | FEAT_MSPHERE>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(render_kernel_v2<false, false, false, 2, FEAT_MEDIA | FEAT_MEDIA_GENERAL>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(render_kernel_v2<false, true, false, 2, FEAT_MEDIA | FEAT_MEDIA_GENERAL>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    for (int k = 0; k < kNumInstances; k++) cudaFuncSetAttribute((const void*)kInstances[k].kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
 #if RT_PARK_STATE  // measurement build: 9 words per thread of parked path state, RT_MIN_BLOCKS blocks per SM
     {
         const int pct = (int)((100 * RT_MIN_BLOCKS * (10 * RT_V2_THREADS * 4 + 2048) + 233471) / 233472);
@@ -1545,6 +1563,9 @@ static int upload_scene_impl(DevCtx* ctx, const rt_scene_desc* sc, bool device_b
     for (int i = 0; i < sc->n_materials; i++)
         if (sc->materials[i].type == RT_MAT_SPECULAR) ctx->scene_feat |= FEAT_SPECULAR;
     if (world_count[PT_MSPHERE] > 0 || !msph.empty()) ctx->scene_feat |= FEAT_MSPHERE;
+    if (!tri.empty() || world_count[PT_TRI] > 0) ctx->scene_feat |= FEAT_TRI;
+    if (sc->n_lights > 0) ctx->scene_feat |= FEAT_LIGHTS;
+    if (sc->camera.defocus_angle > 0) ctx->scene_feat |= FEAT_DEFOCUS;
     ctx->scene_lite = tri.empty() && world_count[PT_TRI] == 0 && sc->n_lights == 0 && !(sc->camera.defocus_angle > 0);
     ctx->cam_w = ctx->cam_h = 0;
     ctx->has_scene = true;
@@ -1947,10 +1968,8 @@ static int launch_wavefront(DevCtx* ctx, const RenderArgs& A, cudaStream_t strea
 }
 #endif
 
-// The instances of render_kernel_v2: variant 0 plain, 1 LITE, 2 STATS, 3 NEE + LITE, 4 NEE; width 2, 4, 8 (3, 4: binary tree
-// only).  Variants 5 + 2 k (plain) and 6 + 2 k (LITE): the binary-tree instance for feature mask kFeatMasks[k].
-typedef void (*RenderKernel)(const DevScene, const RenderArgs, unsigned long long*, unsigned long long*, Stats*);
-static const int kFeatMasks[3] = {0, FEAT_MEDIA | FEAT_MSPHERE, FEAT_MEDIA | FEAT_MEDIA_GENERAL};  // C1/C2/C4, C5, C3; then FEAT_ALL = variants 0 / 1
+// The instances of render_kernel_v2: variant 0 plain (everything), 1 LITE, 2 STATS, 3 NEE + LITE, 4 NEE; width 2, 4, 8
+// (3, 4: binary tree only).  Variants 5 + k: the binary-tree instance kInstances[k], compiled for one feature mask.
 template <int WIDTH>
 static RenderKernel v2_instance(int variant) {
     switch (variant) {
@@ -1965,15 +1984,7 @@ static int v2_effective_width(int variant, int width) { return variant >= 3 ? 2 
 static RenderKernel v2_kernel(int variant, int width) {
     if (variant == 3) return render_kernel_v2<false, true, true, 2>;
     if (variant == 4) return render_kernel_v2<false, false, true, 2>;
-    switch (variant) {
-        case 5: return render_kernel_v2<false, false, false, 2, 0>;
-        case 6: return render_kernel_v2<false, true, false, 2, 0>;
-        case 7: return render_kernel_v2<false, false, false, 2, FEAT_MEDIA | FEAT_MSPHERE>;
-        case 8: return render_kernel_v2<false, true, false, 2, FEAT_MEDIA | FEAT_MSPHERE>;
-        case 9: return render_kernel_v2<false, false, false, 2, FEAT_MEDIA | FEAT_MEDIA_GENERAL>;
-        case 10: return render_kernel_v2<false, true, false, 2, FEAT_MEDIA | FEAT_MEDIA_GENERAL>;
-        default: break;
-    }
+    if (variant >= 5 && variant < 5 + kNumInstances) return kInstances[variant - 5].kernel;
     return width == 8 ? v2_instance<8>(variant) : (width == 4 ? v2_instance<4>(variant) : v2_instance<2>(variant));
 }
 // dynamic shared memory of a wide instance: the traversal stacks, [entry][thread]
@@ -2094,10 +2105,13 @@ static int dev_render(DevCtx* ctx, const rt_render_params* p) {
     const bool want_shadow = (p->flags & RT_FLAG_SHADOWED_POINT_LIGHTS) != 0 && ctx->scene.n_lights > 0;
     int variant = (want_nee || want_shadow) ? (lite ? 3 : 4) : (stats ? 2 : (lite ? 1 : 0));
     const int width = ctx->scene.wide_width ? ctx->scene.wide_width : 2;
-    // the smallest compiled feature mask that covers the scene (RT_B200_NO_MEDIA_INSTANCE=1: always the general instance)
+    // the first compiled instance that covers the scene's features (RT_B200_NO_MEDIA_INSTANCE=1: always a general one)
     if (variant <= 1 && width == 2 && !getenv("RT_B200_NO_MEDIA_INSTANCE"))
-        for (int k = 0; k < 3; k++)
-            if ((ctx->scene_feat & ~kFeatMasks[k]) == 0) { variant += 5 + 2 * k; break; }
+        for (int k = 0; k < kNumInstances; k++)
+            if ((!kInstances[k].lite || lite) && (ctx->scene_feat & ~kInstances[k].feat) == 0) {
+                variant = 5 + k;
+                break;
+            }
     if (ctx->kernel_version == 2) {
         rc = v2_blocks_per_sm(ctx, variant, width, &bps);
         if (rc != RT_OK) return rc;
