@@ -2105,8 +2105,8 @@ static int dev_render(DevCtx* ctx, const rt_render_params* p) {
     const bool want_shadow = (p->flags & RT_FLAG_SHADOWED_POINT_LIGHTS) != 0 && ctx->scene.n_lights > 0;
     int variant = (want_nee || want_shadow) ? (lite ? 3 : 4) : (stats ? 2 : (lite ? 1 : 0));
     const int width = ctx->scene.wide_width ? ctx->scene.wide_width : 2;
-    // the first compiled instance that covers the scene's features (RT_B200_NO_MEDIA_INSTANCE=1: always a general one)
-    if (variant <= 1 && width == 2 && !getenv("RT_B200_NO_MEDIA_INSTANCE"))
+    // the first compiled instance that covers the scene's features (RT_B200_GENERAL_INSTANCE=1: always a general one)
+    if (variant <= 1 && width == 2 && !getenv("RT_B200_GENERAL_INSTANCE"))
         for (int k = 0; k < kNumInstances; k++)
             if ((!kInstances[k].lite || lite) && (ctx->scene_feat & ~kInstances[k].feat) == 0) {
                 variant = 5 + k;

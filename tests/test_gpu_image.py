@@ -259,17 +259,18 @@ def test_box_bounded_media_take_the_slab_test(built, scene_of, monkeypatch):
     assert np.allclose(a.mean(axis=(0, 1)), b.mean(axis=(0, 1)), rtol=2e-3)
 
 
-@pytest.mark.parametrize("name", ["book1", "cornell", "mesh"])
-def test_the_instance_without_media_code_renders_the_same_bits(built, scene_of, monkeypatch, name):
-    """Scenes without a constant_medium run render_kernel_v2<..., MEDIA=false> (no free-flight code compiled in);
-    RT_B200_NO_MEDIA_INSTANCE=1 forces the general instance: same sums."""
+@pytest.mark.parametrize("name", ["book1", "cornell", "cornell_smoke", "mesh", "final", "kitchen_sink"])
+def test_the_feature_instances_render_the_same_bits(built, scene_of, monkeypatch, name):
+    """A scene runs the instance of render_kernel_v2 that carries only the code it can reach (kInstances in rt_b200.cu:
+    one per BASELINE config; kitchen_sink needs the general one); RT_B200_GENERAL_INSTANCE=1 forces the general
+    instance: same sums."""
     sc = scene_of(name)
     out = []
     for forced in (False, True):
         if forced:
-            monkeypatch.setenv("RT_B200_NO_MEDIA_INSTANCE", "1")
+            monkeypatch.setenv("RT_B200_GENERAL_INSTANCE", "1")
         else:
-            monkeypatch.delenv("RT_B200_NO_MEDIA_INSTANCE", raising=False)
+            monkeypatch.delenv("RT_B200_GENERAL_INSTANCE", raising=False)
         c = capi.Context(0)
         try:
             c.upload(sc)
